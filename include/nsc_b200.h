@@ -1,0 +1,179 @@
+/*
+ * nsc_b200.h -- C ABI of the B200-native spectral encoding front end.
+ *
+ * Drop-in boundary for ONE path of Kimun-Park/Neural-Spectral-Codec:
+ *     points -> E x 360 min-range image -> hole interpolation -> row-wise 360-pt
+ *     rFFT magnitude -> n_bins exponential histogram per row -> L1-normalised
+ *     (target_rows * n_bins)-D descriptor.
+ *
+ * The reference has no FFI layer for this path; its boundary is the Python class
+ * SpectralEncoder (reference src/encoding/spectral_encoder.py:24-261) calling
+ * RangeImageProjector.project / interpolate_range_image
+ * (reference src/encoding/range_image.py:129-232, :15-89). Each entry point below
+ * names the reference interface it replaces. The Python host mirror that binds this
+ * header with ctypes is neural_spectral_codec_b200/encoder.py; INTEGRATION.md shows the
+ * stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ or torch types cross this boundary.
+ *   - d_* pointers are CUDA device pointers, h_* pointers are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream). All
+ *     device work is enqueued on it; entry points taking d_* pointers never synchronise.
+ *   - The caller owns every buffer. The library keeps no mutable global state; the only
+ *     per-process caches are immutable device attributes (SM count, occupancy).
+ *   - Every function returns NSC_OK (0) or a negative nsc_status; nothing throws.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point returns
+ *     NSC_ERR_CUDA.
+ */
+#ifndef NSC_B200_H
+#define NSC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSC_ABI_VERSION 1
+#define NSC_N_AZIMUTH 360        /* the in-kernel FFT is a 360-point transform            */
+#define NSC_N_FREQS 181          /* n_azimuth/2 + 1, spectral_encoder.py:88               */
+#define NSC_MAX_ELEVATION 64     /* rows of the projected image held in shared memory     */
+#define NSC_MAX_TARGET_ROWS 64
+#define NSC_MAX_BINS 181
+#define NSC_MAX_DESCRIPTOR 4096  /* target_rows * n_bins held in shared memory             */
+#define NSC_MAX_PEERS 8          /* GPUs of one NVSwitch box written by the fused all-gather */
+
+typedef enum nsc_status {
+    NSC_OK = 0,
+    NSC_ERR_NULL_POINTER = -1,
+    NSC_ERR_BAD_STRIDE = -2,       /* point stride must be 3 or 4 floats                  */
+    NSC_ERR_BAD_COUNT = -3,        /* negative n_scans / n_images                          */
+    NSC_ERR_BAD_PARAMS = -4,       /* nsc_params outside the supported envelope            */
+    NSC_ERR_BAD_LUT = -5,          /* freq->bin table not monotone / out of range          */
+    NSC_ERR_WORKSPACE = -6,        /* workspace missing or too small                       */
+    NSC_ERR_ALIGNMENT = -7,        /* stride-4 points must be 16-byte aligned              */
+    NSC_ERR_BAD_OFFSETS = -8,      /* host offsets not monotone                            */
+    NSC_ERR_CUDA = -9,             /* CUDA runtime error (see nsc_last_cuda_error)         */
+    NSC_ERR_BAD_STRUCT = -10       /* struct_size does not match this ABI                  */
+} nsc_status;
+
+/* Encoder constants. Mirrors the constructor of the reference encoder
+ * (spectral_encoder.py:35-47) and the projector defaults it never forwards
+ * (range_image.py:102-109). POD; set struct_size = sizeof(nsc_params). */
+typedef struct nsc_params {
+    int32_t struct_size;
+    int32_t n_elevation;        /* rows of the projected image, 1..NSC_MAX_ELEVATION       */
+    int32_t n_azimuth;          /* must be NSC_N_AZIMUTH                                    */
+    int32_t n_bins;             /* histogram bins per row, 1..NSC_MAX_BINS                  */
+    int32_t target_rows;        /* target_elevation_bins; rows are average-pooled to this   */
+    int32_t interpolate_empty;  /* 1 = fill empty pixels before the FFT (reference default) */
+    float min_range;            /* 1.0  (range_image.py:108)                                */
+    float max_range;            /* 80.0 (range_image.py:107)                                */
+    double el_min_rad;          /* np.deg2rad(elevation_range[0]) (range_image.py:126)      */
+    double el_max_rad;          /* np.deg2rad(elevation_range[1]) (range_image.py:127)      */
+    float epsilon;              /* 1e-8 (spectral_encoder.py:42)                            */
+    int32_t reserved;
+} nsc_params;
+
+/* Which image nsc_project_batch writes out. */
+#define NSC_STAGE_PROJECTED 0      /* RangeImageProjector.project output (range_image.py:129-214) */
+#define NSC_STAGE_INTERPOLATED 1   /* after interpolate_range_image (range_image.py:15-89)        */
+
+int nsc_abi_version(void);
+const char* nsc_strerror(int status);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char* nsc_last_cuda_error(void);
+/* Fills defaults of the reference constructor for a 16-row encoder. */
+void nsc_default_params(nsc_params* p);
+
+/* freq -> bin table of SpectralEncoder._bin_fft_magnitudes (spectral_encoder.py:136-145)
+ * computed in float32 C arithmetic: edges[i] = (exp(a*i/n_bins)-1)/(exp(a)-1+eps)*n_freqs
+ * (spectral_encoder.py:107-114), bin[k] = clamp(upper_bound(edges, k) - 1, 0, n_bins-1).
+ * The Python host passes the table it computed with the reference's own torch calls; this
+ * function serves non-Python callers and is tested equal to it. h_lut has NSC_N_FREQS ints. */
+int nsc_freq_to_bin(float alpha, const nsc_params* p, int32_t* h_lut);
+
+/* Device workspace needed by nsc_encode_batch / nsc_project_batch (a work counter). */
+size_t nsc_workspace_bytes(int n_scans, const nsc_params* p);
+
+/* Replaces a loop of SpectralEncoder.encode_points (spectral_encoder.py:206-229; callers
+ * src/pipeline.py:245,351, train_multi_dataset.py:182) over n_scans scans.
+ *   d_points   concatenated scans, float32, point_stride (3 or 4) floats per point, AoS
+ *              xyz[i] exactly as the reference loaders produce (kitti_loader.py:100-115)
+ *   d_offsets  int64[n_scans+1] CSR offsets in POINTS; scan i = [offsets[i]-point_origin,
+ *              offsets[i+1]-point_origin) relative to d_points
+ *   h_lut      int32[NSC_N_FREQS] freq->bin table on the HOST (monotone non-decreasing)
+ *   d_out      float32[n_scans * target_rows * n_bins], row-major (scan, row, bin) -- the
+ *              layout of histograms.flatten() (spectral_encoder.py:158)
+ * One fused kernel launch; the range image, its interpolation and the spectrum live in
+ * shared memory only. */
+int nsc_encode_batch(const float* d_points, int point_stride, const int64_t* d_offsets,
+                     int64_t point_origin, int n_scans, const nsc_params* p,
+                     const int32_t* h_lut, float* d_out, void* d_workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* nsc_encode_batch fused with the all-gather that follows it in a multi-GPU encode
+ * (the replicated descriptor database that
+ * WassersteinRetriever.add_to_database, reference src/retrieval/wasserstein.py:300-326, would
+ * hold). Each descriptor is stored by the encode kernel's epilogue straight into row
+ * db_row0 + i of EVERY database in h_peer_db[0..n_peers): host array of device pointers, one
+ * per GPU of the box, peer-mapped into this process (CUDA IPC / symmetric memory), the local
+ * database included. No separate collective pass; the caller synchronises all ranks
+ * afterwards (a barrier), exactly as after an NCCL all-gather. */
+int nsc_encode_batch_peers(const float* d_points, int point_stride, const int64_t* d_offsets,
+                           int64_t point_origin, int n_scans, const nsc_params* p,
+                           const int32_t* h_lut, float* const* h_peer_db, int n_peers,
+                           int64_t db_row0, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces RangeImageProjector.project(points, keep_intensity=False)[0]
+ * (stage = NSC_STAGE_PROJECTED) optionally followed by interpolate_range_image
+ * (stage = NSC_STAGE_INTERPOLATED). d_images: float32[n_scans * n_elevation * 360].
+ * Used by the parity tests and by the projector attribute of the Python mirror. */
+int nsc_project_batch(const float* d_points, int point_stride, const int64_t* d_offsets,
+                      int64_t point_origin, int n_scans, const nsc_params* p, int stage,
+                      float* d_images, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* Replaces SpectralEncoder.forward / encode_batch / encode_range_image
+ * (spectral_encoder.py:160-204, :231-261): range images in, no projection and no
+ * interpolation; rows are average-pooled to target_rows when they differ
+ * (spectral_encoder.py:171-176). d_images: float32[n_images * rows * 360]. */
+int nsc_encode_range_images(const float* d_images, int n_images, int rows, const nsc_params* p,
+                            const int32_t* h_lut, float* d_out, void* stream);
+
+/* Replaces interpolate_range_image(img, 'linear') (range_image.py:15-89) on a batch of
+ * images already on the device. In and out may alias. */
+int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows,
+                                 float* d_images_out, void* stream);
+
+/* ---- host-buffer pipeline (the end-to-end call: H2D, encode, D2H inside) -------------- */
+typedef struct nsc_pipeline nsc_pipeline;
+
+/* Creates a pipeline that stages at most max_chunk_points points per chunk through
+ * n_buffers (2..4) device staging buffers with one stream each. */
+int nsc_pipeline_create(int64_t max_chunk_points, int n_buffers, int device, nsc_pipeline** out);
+void nsc_pipeline_destroy(nsc_pipeline* pl);
+
+/* Same contract as nsc_encode_batch with HOST buffers: h_points (pinned memory gives full
+ * PCIe rate; pageable works), h_offsets int64[n_scans+1] starting at 0, h_out
+ * float32[n_scans * target_rows * n_bins]. Chunks of whole scans are copied H2D, encoded
+ * and copied back D2H on rotating streams so copies overlap compute. Synchronous: returns
+ * when h_out is complete. A scan larger than max_chunk_points returns NSC_ERR_WORKSPACE. */
+int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_stride,
+                        const int64_t* h_offsets, int n_scans, const nsc_params* p,
+                        const int32_t* h_lut, float* h_out);
+
+/* ---- test hooks (not part of the product path) ----------------------------------------- */
+/* Evaluates the kernel's per-point inline function (csrc/nsc_point.h) on the HOST for
+ * n_points points: row / col (or -1) and keep flag per point. It exists so that the CPU-only
+ * test suite can compare the pixel assignment with the oracle without a GPU; it computes no
+ * image and no descriptor, and nothing in the encoder calls it. */
+int nsc_test_host_classify(const float* h_points, int point_stride, int64_t n_points,
+                           const nsc_params* p, int32_t* h_row, int32_t* h_col, uint8_t* h_keep);
+/* 0 = polynomial row assignment, 1 = threshold search (wide fields of view); < 0 = status. */
+int nsc_test_row_mode(const nsc_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSC_B200_H */

@@ -1,0 +1,287 @@
+// extern "C" entry points of libnsc_b200.so (declared in include/nsc_b200.h).
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "nsc_point.h"
+
+namespace nsc {
+
+static thread_local std::string t_cuda_error;
+
+int record_cuda(cudaError_t e) {
+    if (e == cudaSuccess) return NSC_OK;
+    t_cuda_error = std::string(cudaGetErrorName(e)) + ": " + cudaGetErrorString(e);
+    return NSC_ERR_CUDA;
+}
+
+static int check_points(const float* d_points, int stride, const int64_t* d_offsets, int n_scans) {
+    if (n_scans < 0) return NSC_ERR_BAD_COUNT;
+    if (stride != 3 && stride != 4) return NSC_ERR_BAD_STRIDE;
+    if (!d_offsets) return NSC_ERR_NULL_POINTER;
+    if (stride == 4 && (reinterpret_cast<uintptr_t>(d_points) & 15u)) return NSC_ERR_ALIGNMENT;
+    return NSC_OK;
+}
+
+}  // namespace nsc
+
+using namespace nsc;
+
+extern "C" {
+
+const char* nsc_last_cuda_error(void) { return t_cuda_error.c_str(); }
+
+size_t nsc_workspace_bytes(int n_scans, const nsc_params* p) {
+    if (n_scans < 0 || validate_params(p) != NSC_OK) return 0;
+    return workspace_bytes_for(n_scans, p->n_elevation);
+}
+
+int nsc_encode_batch(const float* d_points, int point_stride, const int64_t* d_offsets,
+                     int64_t point_origin, int n_scans, const nsc_params* p, const int32_t* h_lut,
+                     float* d_out, void* d_workspace, size_t workspace_bytes, void* stream) {
+    DeviceParams dp;
+    int st = make_device_params(p, h_lut, &dp);
+    if (st != NSC_OK) return st;
+    st = check_points(d_points, point_stride, d_offsets, n_scans);
+    if (st != NSC_OK) return st;
+    if (n_scans == 0) return NSC_OK;
+    if (!d_out) return NSC_ERR_NULL_POINTER;
+    if (!d_workspace || workspace_bytes < workspace_bytes_for(n_scans, dp.E)) return NSC_ERR_WORKSPACE;
+    return launch_encode(d_points, point_stride, (const long long*)d_offsets, point_origin, n_scans,
+                         dp, d_out, nullptr, 0, nullptr, 0, 0, (unsigned*)d_workspace,
+                         (cudaStream_t)stream);
+}
+
+int nsc_encode_batch_peers(const float* d_points, int point_stride, const int64_t* d_offsets,
+                           int64_t point_origin, int n_scans, const nsc_params* p,
+                           const int32_t* h_lut, float* const* h_peer_db, int n_peers,
+                           int64_t db_row0, void* d_workspace, size_t workspace_bytes, void* stream) {
+    DeviceParams dp;
+    int st = make_device_params(p, h_lut, &dp);
+    if (st != NSC_OK) return st;
+    st = check_points(d_points, point_stride, d_offsets, n_scans);
+    if (st != NSC_OK) return st;
+    if (n_peers < 1 || n_peers > NSC_MAX_PEERS) return NSC_ERR_BAD_COUNT;
+    if (!h_peer_db) return NSC_ERR_NULL_POINTER;
+    for (int i = 0; i < n_peers; ++i)
+        if (!h_peer_db[i]) return NSC_ERR_NULL_POINTER;
+    if (n_scans == 0) return NSC_OK;
+    if (!d_workspace || workspace_bytes < workspace_bytes_for(n_scans, dp.E)) return NSC_ERR_WORKSPACE;
+    return launch_encode(d_points, point_stride, (const long long*)d_offsets, point_origin, n_scans,
+                         dp, nullptr, nullptr, 0, h_peer_db, n_peers, db_row0,
+                         (unsigned*)d_workspace, (cudaStream_t)stream);
+}
+
+int nsc_project_batch(const float* d_points, int point_stride, const int64_t* d_offsets,
+                      int64_t point_origin, int n_scans, const nsc_params* p, int stage,
+                      float* d_images, void* d_workspace, size_t workspace_bytes, void* stream) {
+    // The projection does not depend on the bin table: use the identity-to-zero table.
+    int32_t lut[NSC_N_FREQS];
+    memset(lut, 0, sizeof(lut));
+    DeviceParams dp;
+    int st = make_device_params(p, lut, &dp);
+    if (st != NSC_OK) return st;
+    st = check_points(d_points, point_stride, d_offsets, n_scans);
+    if (st != NSC_OK) return st;
+    if (stage != NSC_STAGE_PROJECTED && stage != NSC_STAGE_INTERPOLATED) return NSC_ERR_BAD_PARAMS;
+    if (n_scans == 0) return NSC_OK;
+    if (!d_images) return NSC_ERR_NULL_POINTER;
+    if (!d_workspace || workspace_bytes < workspace_bytes_for(n_scans, dp.E)) return NSC_ERR_WORKSPACE;
+    return launch_encode(d_points, point_stride, (const long long*)d_offsets, point_origin, n_scans,
+                         dp, nullptr, d_images, stage, nullptr, 0, 0, (unsigned*)d_workspace,
+                         (cudaStream_t)stream);
+}
+
+int nsc_encode_range_images(const float* d_images, int n_images, int rows, const nsc_params* p,
+                            const int32_t* h_lut, float* d_out, void* stream) {
+    DeviceParams dp;
+    int st = make_device_params(p, h_lut, &dp);
+    if (st != NSC_OK) return st;
+    if (n_images < 0) return NSC_ERR_BAD_COUNT;
+    if (rows < 1 || rows > NSC_MAX_ELEVATION) return NSC_ERR_BAD_PARAMS;
+    if (n_images == 0) return NSC_OK;
+    if (!d_images || !d_out) return NSC_ERR_NULL_POINTER;
+    return launch_encode_images(d_images, n_images, rows, dp, d_out, (cudaStream_t)stream);
+}
+
+int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows,
+                                 float* d_images_out, void* stream) {
+    if (n_images < 0) return NSC_ERR_BAD_COUNT;
+    if (rows < 1 || rows > NSC_MAX_ELEVATION) return NSC_ERR_BAD_PARAMS;
+    if (n_images == 0) return NSC_OK;
+    if (!d_images_in || !d_images_out) return NSC_ERR_NULL_POINTER;
+    return launch_interpolate(d_images_in, n_images, rows, d_images_out, (cudaStream_t)stream);
+}
+
+/* ---- host-buffer pipeline ------------------------------------------------------------- */
+struct nsc_pipeline {
+    int device;
+    int n_buffers;
+    int64_t max_chunk_points;
+    int max_chunk_scans;
+    struct Slot {
+        cudaStream_t stream;
+        cudaEvent_t done;
+        float* d_points;
+        long long* d_offsets;
+        float* d_out;
+        unsigned* d_ws;
+        bool busy;
+    } slot[4];
+};
+
+static const int kMaxChunkScans = 1024;
+static const int kMaxDescriptor = NSC_MAX_DESCRIPTOR;
+
+void nsc_pipeline_destroy(nsc_pipeline* pl) {
+    if (!pl) return;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(pl->device);
+    for (int i = 0; i < pl->n_buffers; ++i) {
+        nsc_pipeline::Slot& s = pl->slot[i];
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.d_points) cudaFree(s.d_points);
+        if (s.d_offsets) cudaFree(s.d_offsets);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_ws) cudaFree(s.d_ws);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaSetDevice(prev);
+    delete pl;
+}
+
+int nsc_pipeline_create(int64_t max_chunk_points, int n_buffers, int device, nsc_pipeline** out) {
+    if (!out) return NSC_ERR_NULL_POINTER;
+    *out = nullptr;
+    if (max_chunk_points < 1 || n_buffers < 1 || n_buffers > 4) return NSC_ERR_BAD_COUNT;
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return record_cuda(e);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) return record_cuda(e);
+    nsc_pipeline* pl = new nsc_pipeline();
+    memset(pl, 0, sizeof(*pl));
+    pl->device = device;
+    pl->n_buffers = n_buffers;
+    pl->max_chunk_points = max_chunk_points;
+    pl->max_chunk_scans = kMaxChunkScans;
+    int st = NSC_OK;
+    for (int i = 0; i < n_buffers && st == NSC_OK; ++i) {
+        nsc_pipeline::Slot& s = pl->slot[i];
+        if ((e = cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming)) != cudaSuccess ||
+            (e = cudaMalloc(&s.d_points, (size_t)max_chunk_points * 16)) != cudaSuccess ||
+            (e = cudaMalloc(&s.d_offsets, (size_t)(kMaxChunkScans + 1) * 8)) != cudaSuccess ||
+            (e = cudaMalloc(&s.d_out, (size_t)kMaxChunkScans * kMaxDescriptor * 4)) != cudaSuccess ||
+            (e = cudaMalloc(&s.d_ws, 256)) != cudaSuccess)
+            st = record_cuda(e);
+    }
+    cudaSetDevice(prev);
+    if (st != NSC_OK) {
+        nsc_pipeline_destroy(pl);
+        return st;
+    }
+    *out = pl;
+    return NSC_OK;
+}
+
+int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_stride,
+                        const int64_t* h_offsets, int n_scans, const nsc_params* p,
+                        const int32_t* h_lut, float* h_out) {
+    if (!pl) return NSC_ERR_NULL_POINTER;
+    DeviceParams dp;
+    int st = make_device_params(p, h_lut, &dp);
+    if (st != NSC_OK) return st;
+    if (n_scans < 0) return NSC_ERR_BAD_COUNT;
+    if (point_stride != 3 && point_stride != 4) return NSC_ERR_BAD_STRIDE;
+    if (n_scans == 0) return NSC_OK;
+    if (!h_points || !h_offsets || !h_out) return NSC_ERR_NULL_POINTER;
+    for (int i = 0; i < n_scans; ++i)
+        if (h_offsets[i + 1] < h_offsets[i]) return NSC_ERR_BAD_OFFSETS;
+    const int D = dp.T * dp.n_bins;
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return record_cuda(e);
+    e = cudaSetDevice(pl->device);
+    if (e != cudaSuccess) return record_cuda(e);
+
+    int first = 0, k = 0;
+    while (first < n_scans && st == NSC_OK) {
+        // chunk = as many whole scans as fit the staging buffer
+        int last = first;
+        while (last < n_scans && last - first < pl->max_chunk_scans &&
+               h_offsets[last + 1] - h_offsets[first] <= pl->max_chunk_points)
+            ++last;
+        if (last == first) { st = NSC_ERR_WORKSPACE; break; }
+        nsc_pipeline::Slot& s = pl->slot[k % pl->n_buffers];
+        if (s.busy) {   // host offsets / output of the previous use must be complete
+            if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) { st = record_cuda(e); break; }
+            s.busy = false;
+        }
+        const int64_t p0 = h_offsets[first], np = h_offsets[last] - p0;
+        const int ns = last - first;
+        const size_t pbytes = (size_t)np * point_stride * 4;
+        if ((e = cudaMemcpyAsync(s.d_points, h_points + p0 * point_stride, pbytes,
+                                 cudaMemcpyHostToDevice, s.stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(s.d_offsets, h_offsets + first, (size_t)(ns + 1) * 8,
+                                 cudaMemcpyHostToDevice, s.stream)) != cudaSuccess) {
+            st = record_cuda(e);
+            break;
+        }
+        st = launch_encode(s.d_points, point_stride, s.d_offsets, p0, ns, dp, s.d_out, nullptr, 0,
+                           nullptr, 0, 0, s.d_ws, s.stream);
+        if (st != NSC_OK) break;
+        if ((e = cudaMemcpyAsync(h_out + (size_t)first * D, s.d_out, (size_t)ns * D * 4,
+                                 cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess ||
+            (e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) {
+            st = record_cuda(e);
+            break;
+        }
+        s.busy = true;
+        first = last;
+        ++k;
+    }
+    for (int i = 0; i < pl->n_buffers; ++i) {
+        nsc_pipeline::Slot& s = pl->slot[i];
+        if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess && st == NSC_OK) st = record_cuda(e);
+        s.busy = false;
+    }
+    cudaSetDevice(prev);
+    return st;
+}
+
+/* ---- test hook: the kernel's per-point function evaluated on the host ------------------ */
+int nsc_test_host_classify(const float* h_points, int point_stride, int64_t n_points,
+                           const nsc_params* p, int32_t* h_row, int32_t* h_col, uint8_t* h_keep) {
+    int32_t lut[NSC_N_FREQS];
+    memset(lut, 0, sizeof(lut));
+    DeviceParams dp;
+    int st = make_device_params(p, lut, &dp);
+    if (st != NSC_OK) return st;
+    if (point_stride != 3 && point_stride != 4) return NSC_ERR_BAD_STRIDE;
+    if (n_points < 0) return NSC_ERR_BAD_COUNT;
+    if (n_points && (!h_points || !h_row || !h_col || !h_keep)) return NSC_ERR_NULL_POINTER;
+    for (int64_t i = 0; i < n_points; ++i) {
+        const float* q = h_points + i * point_stride;
+        uint32_t pix = 0, sb = 0;
+        const bool keep = classify(q[0], q[1], q[2], dp, dp.row_mode, pix, sb);
+        h_keep[i] = keep ? 1 : 0;
+        h_row[i] = keep ? (int32_t)(pix / kPitch) : -1;
+        int32_t c = keep ? (int32_t)(pix % kPitch) : -1;
+        h_col[i] = c == kAz ? 0 : c;
+    }
+    return NSC_OK;
+}
+
+int nsc_test_row_mode(const nsc_params* p) {
+    int32_t lut[NSC_N_FREQS];
+    memset(lut, 0, sizeof(lut));
+    DeviceParams dp;
+    int st = make_device_params(p, lut, &dp);
+    return st != NSC_OK ? st : dp.row_mode;
+}
+
+}  // extern "C"

@@ -1,0 +1,286 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's recorded
+outputs. Run on the B200 box: ``python -m pytest tests -m gpu``.
+
+Tolerances (BASELINE.json north_star):
+  * pixel assignment / range image: bit-exact once points within 1e-5 rad of a row or column
+    edge are removed; with them, at most one differing pixel per such point;
+  * interpolation, keep/drop, freq->bin table: bit-exact;
+  * descriptor: allclose(rtol=1e-4, atol=1e-7) and ||gpu - ref||_2 <= 1e-5 ||ref||_2.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle import nsc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+RTOL, ATOL, L2REL = 1e-4, 1e-7, 1e-5
+
+POINT_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
+                     if not os.path.basename(p).startswith("forward_"))
+CTOR = {"elev64_pooled": dict(n_elevation=64), "elev64_sparse": dict(n_elevation=64),
+        "no_interp": dict(interpolate_empty=False)}
+
+
+def make_encoder(**kw):
+    from neural_spectral_codec_b200 import SpectralEncoder
+    args = dict(n_elevation=16, n_azimuth=360, n_bins=50, alpha=2.0, learnable_alpha=True,
+                target_elevation_bins=16)
+    args.update(kw)
+    return SpectralEncoder(**args).to("cuda")
+
+
+def assert_descriptor(got, ref):
+    got = np.asarray(got, np.float64)
+    ref = np.asarray(ref, np.float64)
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=ATOL)
+    assert np.linalg.norm(got - ref) <= L2REL * np.linalg.norm(ref)
+
+
+def n_ambiguous(points, cfg):
+    if len(points) == 0:
+        return 0
+    d_az, d_el = orc.edge_distance(points, cfg)
+    return int(((d_az <= 1e-5) | (d_el <= 1e-5)).sum())
+
+
+@pytest.mark.parametrize("name", POINT_CASES)
+def test_golden_case(name):
+    """Every recorded reference case: range image, interpolated image, descriptor."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    kw = CTOR.get(name, {})
+    enc = make_encoder(**kw)
+    cfg = orc.OracleConfig(**kw)
+    pts = g["points"]
+
+    np.testing.assert_array_equal(enc.freq_to_bin(), g["freq_to_bin"])
+
+    img, _ = enc.projector.project(pts, keep_intensity=False)
+    assert img.shape == g["range_image"].shape and img.dtype == np.float32
+    diff = int((img != g["range_image"]).sum())
+    assert diff <= n_ambiguous(pts, cfg), f"{diff} pixels differ"
+
+    # hole interpolation of the GPU's own projected image must equal the oracle's, bit for bit
+    if cfg.interpolate_empty:
+        dpts = torch.from_numpy(np.ascontiguousarray(pts, np.float32)).cuda()
+        offs = torch.tensor([0, len(pts)])
+        filled = enc.projector.project_batch(dpts, offs, interpolate=True)[0].cpu().numpy()
+        np.testing.assert_array_equal(filled, orc.interpolate_range_image(img))
+        if diff == 0:
+            np.testing.assert_array_equal(filled, g["interpolated"])
+
+    d = enc.encode_points(pts)
+    assert d.shape == (enc.output_dim,) and d.dtype == torch.float32 and d.is_cuda
+    assert not d.requires_grad
+    if diff == 0:
+        assert_descriptor(d.cpu().numpy(), g["descriptor"])
+    else:   # a moved edge point changes the image; compare through the oracle tail instead
+        ref = orc.encode_range_image(torch.from_numpy(
+            orc.interpolate_range_image(img) if cfg.interpolate_empty else img), cfg).numpy()
+        assert_descriptor(d.cpu().numpy(), ref)
+        assert np.abs(d.cpu().numpy() - g["descriptor"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["hdl64_full", "hdl32_small", "beam128_small", "hdl64_small_shuffled"])
+def test_stripped_cloud_is_bit_exact(name):
+    """P1: without the excused edge points the range image is bit-identical to the oracle."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = orc.OracleConfig()
+    enc = make_encoder()
+    pts = orc.strip_ambiguous(g["points"], cfg)
+    img, _ = enc.projector.project(pts, keep_intensity=False)
+    np.testing.assert_array_equal(img, orc.project(pts, cfg))
+    assert_descriptor(enc.encode_points(pts).cpu().numpy(), orc.encode_points(pts, cfg).numpy())
+
+
+def test_interpolate_entry_matches_reference_vectors():
+    from neural_spectral_codec_b200 import interpolate_range_image
+    for name in POINT_CASES:
+        g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        if name == "no_interp":
+            continue
+        np.testing.assert_array_equal(interpolate_range_image(g["range_image"]), g["interpolated"])
+    rng = np.random.default_rng(5)
+    imgs = (rng.uniform(1, 60, (40, 16, 360)) * (rng.uniform(0, 1, (40, 16, 360)) > 0.7)).astype(np.float32)
+    imgs[3, 4:9] = 0
+    imgs[5, :3] = 0
+    imgs[6, 13:] = 0
+    imgs[7] = 0
+    imgs[8, 2] = 0
+    imgs[8, 2, 77] = 5.5    # single valid pixel -> constant row
+    got = interpolate_range_image(imgs)
+    for i in range(len(imgs)):
+        np.testing.assert_array_equal(got[i], orc.interpolate_range_image(imgs[i]))
+
+
+def test_forward_on_range_images():
+    g = np.load(os.path.join(GOLDEN_DIR, "forward_batches.npz"))
+    for key, rows in (("16", 16), ("64", 64), ("40", 40)):
+        enc = make_encoder(n_elevation=rows)
+        d = enc(torch.from_numpy(g["imgs" + key]).cuda())
+        assert d.shape == (g["imgs" + key].shape[0], 800)
+        for i in range(d.shape[0]):
+            assert_descriptor(d[i].cpu().numpy(), g["desc" + key][i])
+        one = enc.encode_range_image(torch.from_numpy(g["imgs" + key][0]).cuda())
+        np.testing.assert_array_equal(one.cpu().numpy(), d[0].cpu().numpy())
+        np.testing.assert_array_equal(enc.encode_batch(torch.from_numpy(g["imgs" + key]).cuda()).cpu().numpy(),
+                                      d.cpu().numpy())
+
+
+def test_batch_equals_single_and_is_deterministic():
+    from neural_spectral_codec_b200 import synth
+    small = synth.SensorShape("s", 64, -24.8, 2.0, 700)
+    pts, offs = synth.make_batch(small, 10, 37)
+    enc = make_encoder()
+    dpts, doffs = pts.cuda(), offs.cuda()
+    a = enc.encode_points_batch(dpts, doffs).cpu().numpy()
+    b = enc.encode_points_batch(dpts, doffs).cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    o = offs.numpy()
+    cfg = orc.OracleConfig()
+    for i in (0, 5, 36):
+        s = pts[o[i]:o[i + 1]].numpy()
+        np.testing.assert_array_equal(enc.encode_points(s).cpu().numpy(), a[i])
+        assert np.abs(a[i] - orc.encode_points(s, cfg).numpy()).max() < 1e-4
+    # shuffled point order gives the same min image, hence the same bits
+    perm = torch.randperm(int(o[1]), generator=torch.Generator().manual_seed(0))
+    np.testing.assert_array_equal(enc.encode_points(pts[:o[1]][perm].numpy()).cpu().numpy(), a[0])
+
+
+def test_ragged_batch_with_empty_and_filtered_scans():
+    enc = make_encoder()
+    cfg = orc.OracleConfig()
+    g = np.load(os.path.join(GOLDEN_DIR, "hdl32_small.npz"))["points"]
+    scans = [g[:5000], np.zeros((0, 4), np.float32), g[5000:5001],
+             np.full((7, 4), np.nan, np.float32), np.array([[500, 0, 0, 0]], np.float32), g[6000:]]
+    offs = np.cumsum([0] + [len(s) for s in scans])
+    pts = torch.from_numpy(np.concatenate(scans)).cuda()
+    d = enc.encode_points_batch(pts, torch.from_numpy(offs)).cpu().numpy()
+    uniform = np.full(800, np.float32(1.0) / np.float32(800))
+    for i in (1, 3, 4):
+        np.testing.assert_array_equal(d[i], uniform)
+    for i in (0, 2, 5):
+        ref = orc.encode_points(scans[i], cfg).numpy()
+        assert np.abs(d[i] - ref).max() < 1e-4
+    one = d[2].reshape(16, 50)
+    np.testing.assert_allclose(one[:, 0], 0.0625, rtol=1e-6)
+    assert np.abs(one[:, 1:]).max() < 1e-7
+
+
+def test_xyz_only_stride3_equals_xyzi():
+    g = np.load(os.path.join(GOLDEN_DIR, "hdl64_small_shuffled.npz"))["points"]
+    enc = make_encoder()
+    a = enc.encode_points(g).cpu().numpy()
+    b = enc.encode_points(np.ascontiguousarray(g[:, :3])).cpu().numpy()
+    np.testing.assert_array_equal(a, b)
+    # odd scan starts exercise unaligned 12-byte rows
+    xyz = torch.from_numpy(np.ascontiguousarray(g[:, :3])).cuda()
+    offs = torch.tensor([0, 1, 1001, 7778, len(g)])
+    d3 = enc.encode_points_batch(xyz, offs).cpu().numpy()
+    d4 = enc.encode_points_batch(torch.from_numpy(g).cuda(), offs).cpu().numpy()
+    np.testing.assert_array_equal(d3, d4)
+
+
+def test_wide_field_of_view_uses_threshold_rows():
+    """elevation_range beyond the polynomial's span switches the row rule to the threshold
+    search; both must agree with the oracle away from edges."""
+    rng = np.random.default_rng(3)
+    n = 40000
+    az = rng.uniform(-np.pi, np.pi, n)
+    el = rng.uniform(-1.4, 1.4, n)
+    r = rng.uniform(1.5, 70, n)
+    pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el),
+                    np.zeros(n)], 1).astype(np.float32)
+    for er, rows in (((-60.0, 60.0), 32), ((-15.0, 15.0), 16), ((-89.0, 89.0), 64)):
+        enc = make_encoder(n_elevation=rows, elevation_range=er)
+        cfg = orc.OracleConfig(n_elevation=rows, elevation_range=er)
+        s = orc.strip_ambiguous(pts, cfg)
+        img, _ = enc.projector.project(s, keep_intensity=False)
+        np.testing.assert_array_equal(img, orc.project(s, cfg))
+
+
+def test_host_pipeline_equals_device_batch():
+    from neural_spectral_codec_b200 import synth
+    small = synth.SensorShape("s", 64, -24.8, 2.0, 900)
+    pts, offs = synth.make_batch(small, 100, 23)
+    enc = make_encoder()
+    ref = enc.encode_points_batch(pts.cuda(), offs.cuda()).cpu().numpy()
+    o = offs.numpy()
+    scans = [pts[o[i]:o[i + 1]].numpy() for i in range(23)]
+    # small chunks force several rotations of the staging buffers
+    got = enc.encode_scans(scans, max_chunk_points=3 * int(np.diff(o).max()), n_buffers=2)
+    np.testing.assert_array_equal(got, ref)
+    pinned = pts.pin_memory()
+    got2 = enc.encode_scans((pinned.numpy(), o))
+    np.testing.assert_array_equal(got2, ref)
+
+
+def test_rotation_invariance_property():
+    """spectral_encoder.py:365-415 with the bound of configs/inference.yaml:99-101."""
+    from neural_spectral_codec_b200 import test_rotation_invariance as rot
+    g = np.load(os.path.join(GOLDEN_DIR, "hdl64_small_shuffled.npz"))["points"]
+    assert rot(make_encoder(), g, 8) < 1e-3
+
+
+def test_full_size_batch_properties():
+    """BASELINE-size scans (120 k points): descriptors are normalised, deterministic, equal to
+    the single-scan call, and a sample is checked against the oracle."""
+    from neural_spectral_codec_b200 import synth
+    pts, offs = synth.make_batch(synth.HDL64, 0, 24, device="cuda")
+    enc = make_encoder()
+    d = enc.encode_points_batch(pts, offs)
+    torch.cuda.synchronize()
+    dn = d.cpu().numpy()
+    assert np.isfinite(dn).all() and (dn >= 0).all()
+    np.testing.assert_allclose(dn.sum(1), 1.0, rtol=0, atol=2e-6)
+    np.testing.assert_array_equal(enc.encode_points_batch(pts, offs).cpu().numpy(), dn)
+    o = offs.cpu().numpy()
+    cfg = orc.OracleConfig()
+    for i in (0, 11, 23):
+        s = pts[o[i]:o[i + 1]].cpu().numpy()
+        assert np.abs(dn[i] - orc.encode_points(s, cfg).numpy()).max() < 1e-4
+        st = orc.strip_ambiguous(s, cfg)
+        assert_descriptor(enc.encode_points(st).cpu().numpy(), orc.encode_points(st, cfg).numpy())
+    for shape in (synth.HDL32, synth.BEAM128):
+        p2, o2 = synth.make_batch(shape, 3, 2, device="cuda")
+        d2 = enc.encode_points_batch(p2, o2).cpu().numpy()
+        oo = o2.cpu().numpy()
+        st = orc.strip_ambiguous(p2[:oo[1]].cpu().numpy(), cfg)
+        assert_descriptor(enc.encode_points(st).cpu().numpy(), orc.encode_points(st, cfg).numpy())
+        assert np.abs(d2[0] - orc.encode_points(p2[:oo[1]].cpu().numpy(), cfg).numpy()).max() < 1e-4
+
+
+def test_error_statuses_through_the_abi():
+    import ctypes as C
+    from neural_spectral_codec_b200 import _lib
+    lib = _lib.load()
+    enc = make_encoder()
+    p = enc._params()
+    lut = enc.freq_to_bin()
+    pts = torch.zeros(16, 4, device="cuda")
+    offs = torch.tensor([0, 16], device="cuda")
+    out = torch.zeros(1, 800, device="cuda")
+    ws = torch.zeros(64, dtype=torch.int32, device="cuda")
+    call = lambda stride=4, n=1, pp=p, l=lut, ptr=pts.data_ptr(), wsz=256: lib.nsc_encode_batch(
+        ptr, stride, offs.data_ptr(), 0, n, C.byref(pp), l.ctypes.data, out.data_ptr(),
+        ws.data_ptr(), wsz, None)
+    assert call() == 0
+    assert call(stride=5) == -2
+    assert call(n=-1) == -3
+    assert call(wsz=4) == -6
+    assert call(ptr=pts.data_ptr() + 4) == -7
+    bad = enc._params()
+    bad.n_azimuth = 361
+    assert call(pp=bad) == -4
+    bad = enc._params()
+    bad.struct_size = 8
+    assert call(pp=bad) == -10
+    bl = lut.copy()
+    bl[5] = 49
+    assert call(l=bl) == -5
+    torch.cuda.synchronize()
