@@ -308,7 +308,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=N_SCANS, help="scans per GPU")
     ap.add_argument("--e2e-scans", type=int, default=1024, help="scans per end-to-end step")
-    ap.add_argument("--gather", default="nccl", choices=["nccl", "fused"])
+    ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -2,6 +2,9 @@
 // -> descriptor. One persistent CTA per resident slot; each CTA pulls whole scans from a work
 // counter, so the range image, its interpolation and the spectrum never leave shared memory:
 // HBM traffic is the 16 B per point and the descriptor.
+#include <stdlib.h>
+#include <string.h>
+
 #include <mutex>
 
 #include "nsc_point.h"
@@ -11,7 +14,8 @@ namespace nsc {
 
 namespace {
 
-constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread
+constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread (LDG feed)
+constexpr int kDefaultFeed = 0;   // kFeedLdg until the TMA ring is measured faster
 
 struct EncodeArgs {
     const float* points;
@@ -31,12 +35,46 @@ __device__ __forceinline__ void scatter_min(uint32_t* img, bool keep, uint32_t p
     if (keep && sbits < img[pix]) atomicMin(img + pix, sbits);
 }
 
-template <int STRIDE, int ROWMODE>
+enum Feed { kFeedLdg = 0, kFeedTma = 1 };
+
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (SASS UBLKCP), completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+
+template <int STRIDE, int ROWMODE, int FEED>
 __global__ void __launch_bounds__(kThreads, 2)
 encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_scan;
-    const SmemLayout L(dp.E, dp.T, dp.n_bins);
+    const SmemLayout L(dp.E, dp.T, dp.n_bins, FEED == kFeedTma);
     const TailSmem S(smem_raw, L);
     uint32_t* img = reinterpret_cast<uint32_t*>(S.img);
     const int tid = threadIdx.x;
@@ -44,6 +82,21 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
     const int D = dp.T * dp.n_bins;
 
     init_twiddles(S.tw);
+
+    // TMA feed: every warp owns kStages x kStageBytes of the ring and one mbarrier per stage.
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t ring0 = smem_u32(smem_raw + L.ring_off) + warp * (kStages * kStageBytes);
+    const uint32_t bar0 = smem_u32(smem_raw + L.bar_off) + warp * (kStages * 8);
+    const float4* ring_w = reinterpret_cast<const float4*>(smem_raw + L.ring_off) +
+                           warp * (kStages * kStagePts);
+    uint32_t g_issue = 0, g_cons = 0;   // chunks issued / consumed by this warp since launch
+    if (FEED == kFeedTma) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
 
     for (;;) {
         __syncthreads();
@@ -56,7 +109,51 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
         const long long beg = a.offsets[scan] - a.origin;
         const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
 
-        if (STRIDE == 4) {
+        if (FEED == kFeedTma) {
+            // Chunk c of the scan (kStagePts points) belongs to warp c % kWarps. Each warp keeps
+            // kStages bulk copies in flight into its own ring; lane 0 arms the stage's mbarrier
+            // with the byte count and issues the copy, all lanes wait on the phase parity.
+            const float4* p4 = reinterpret_cast<const float4*>(a.points) + beg;
+            const int n_chunks = (n + kStagePts - 1) / kStagePts;
+            const int mine = n_chunks > warp ? (n_chunks - warp + kWarps - 1) / kWarps : 0;
+            // The ring doubles as FFT scratch in the tail: order those generic-proxy writes
+            // before the async-proxy writes of the copies issued below.
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            auto issue = [&](int j) {
+                const int c = warp + j * kWarps;
+                const int pts = min(kStagePts, n - c * kStagePts);
+                const uint32_t slot = g_issue % kStages;
+                if (lane == 0) {
+                    mbar_expect_tx(bar0 + 8 * slot, (uint32_t)pts * 16u);
+                    bulk_copy_g2s(ring0 + slot * kStageBytes, p4 + (long long)c * kStagePts,
+                                  (uint32_t)pts * 16u, bar0 + 8 * slot);
+                }
+                ++g_issue;
+            };
+            int issued = 0;
+            for (; issued < mine && issued < kStages; ++issued) issue(issued);
+            for (int j = 0; j < mine; ++j) {
+                const uint32_t slot = g_cons % kStages, parity = (g_cons / kStages) & 1u;
+                mbar_wait(bar0 + 8 * slot, parity);
+                ++g_cons;
+                const int c = warp + j * kWarps;
+                const int valid = min(kStagePts, n - c * kStagePts);
+                const float4* st = ring_w + slot * kStagePts + 3 * lane;
+                const float4 v0 = st[0], v1 = st[1], v2 = st[2];
+                uint32_t p0, p1, p2, s0, s1, s2;
+                bool k0 = classify(v0.x, v0.y, v0.z, dp, ROWMODE, p0, s0) && (3 * lane + 0 < valid);
+                bool k1 = classify(v1.x, v1.y, v1.z, dp, ROWMODE, p1, s1) && (3 * lane + 1 < valid);
+                bool k2 = classify(v2.x, v2.y, v2.z, dp, ROWMODE, p2, s2) && (3 * lane + 2 < valid);
+                // consecutive points of a spinning sensor mostly share a pixel: fold them first
+                if (k0 && k1 && p0 == p1) { s1 = min(s0, s1); k0 = false; }
+                if (k1 && k2 && p1 == p2) { s2 = min(s1, s2); k1 = false; }
+                scatter_min(img, k0, p0, s0);
+                scatter_min(img, k1, p1, s1);
+                scatter_min(img, k2, p2, s2);
+                __syncwarp();   // every lane has read the stage before it is refilled
+                if (issued < mine) issue(issued++);
+            }
+        } else if (STRIDE == 4) {
             const float4* p4 = reinterpret_cast<const float4*>(a.points) + beg;
             for (int base = 0; base < n; base += kThreads * kUnroll) {
                 float4 v[kUnroll];
@@ -238,14 +335,27 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     a.peers.row0 = peer_row0;
     for (int i = 0; i < NSC_MAX_PEERS; ++i) a.peers.ptr[i] = i < n_peers ? d_peer_out[i] : nullptr;
 
-    const SmemLayout L(dp.E, dp.T, dp.n_bins);
+    // Feed of the point pass: per-warp TMA bulk-copy ring (4-float points) or plain vector
+    // loads (3-float points are not 16-byte granular). NSC_FEED=ldg|tma overrides for A/B runs.
+    static const int feed_override = [] {
+        const char* e = getenv("NSC_FEED");
+        if (!e) return -1;
+        return strcmp(e, "tma") == 0 ? (int)kFeedTma : strcmp(e, "ldg") == 0 ? (int)kFeedLdg : -1;
+    }();
+    int feed = kDefaultFeed;
+    if (feed_override >= 0) feed = feed_override;
+    if (stride != 4) feed = kFeedLdg;
+    const SmemLayout L(dp.E, dp.T, dp.n_bins, feed == kFeedTma);
     void (*kernel)(const EncodeArgs, const DeviceParams) = nullptr;
-    if (stride == 4) {
-        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly>
-                                         : encode_points_kernel<4, kRowSearch>;
+    if (feed == kFeedTma) {
+        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedTma>
+                                         : encode_points_kernel<4, kRowSearch, kFeedTma>;
+    } else if (stride == 4) {
+        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedLdg>
+                                         : encode_points_kernel<4, kRowSearch, kFeedLdg>;
     } else {
-        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<3, kRowPoly>
-                                         : encode_points_kernel<3, kRowSearch>;
+        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<3, kRowPoly, kFeedLdg>
+                                         : encode_points_kernel<3, kRowSearch, kFeedLdg>;
     }
     int per_sm = 0;
     st = configure(kernel, L.total, di, &per_sm);

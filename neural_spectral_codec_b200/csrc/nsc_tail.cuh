@@ -12,18 +12,35 @@ namespace nsc {
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 
-// Shared-memory carve-up, identical on host (size) and device (pointers).
+// Per-warp bulk-copy ring of the point pass (TMA feed): kStages stages of kStagePts points.
+constexpr int kStagePts = 96;            // 3 consecutive points per lane: 48-byte lane stride is
+                                         // conflict-free for 16-byte shared loads
+constexpr int kStages = 3;
+constexpr int kStageBytes = kStagePts * 16;
+constexpr int kRingBytes = kWarps * kStages * kStageBytes;   // 73 728 B per CTA
+
+// Shared-memory carve-up, identical on host (size) and device (pointers). With a ring the two
+// FFT buffers alias it: the ring is idle (fully consumed) while the tail runs.
 struct SmemLayout {
-    int img_off, tw_off, fa_off, fb_off, hist_off, mask_off, nvalid_off, src_off, red_off, total;
+    int img_off, tw_off, fa_off, fb_off, hist_off, mask_off, nvalid_off, src_off, red_off;
+    int ring_off, bar_off, total;
     int n_sig;  // complex FFTs per batch
-    __host__ __device__ SmemLayout(int rows, int T, int n_bins) {
+    __host__ __device__ SmemLayout(int rows, int T, int n_bins, bool ring = false) {
         int o = 0;
-        auto take = [&o](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+        auto take = [&o](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
         n_sig = (T + 1) / 2 < kMaxSignals ? (T + 1) / 2 : kMaxSignals;
         img_off = take(rows * kPitch * 4);
         tw_off = take(kAz * 8);
-        fa_off = take(n_sig * kAz * 8);
-        fb_off = take(n_sig * kAz * 8);
+        if (ring) {
+            ring_off = take(kRingBytes);
+            fa_off = ring_off;
+            fb_off = ring_off + n_sig * kAz * 8;      // 2 * 8 * 2880 = 46 080 <= kRingBytes
+            bar_off = take(kWarps * kStages * 8);
+        } else {
+            ring_off = bar_off = 0;
+            fa_off = take(n_sig * kAz * 8);
+            fb_off = take(n_sig * kAz * 8);
+        }
         hist_off = take(T * n_bins * 4);
         mask_off = take(rows * kMaskWords * 4);
         nvalid_off = take(rows * 4);
