@@ -12,7 +12,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnsc_b200.so")
+# NSC_LIB selects a tuning build (csrc/Makefile VARIANT=...); the default is the product library.
+LIB_PATH = os.environ.get("NSC_LIB") or os.path.join(_HERE, "libnsc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 NSC_ABI_VERSION = 1

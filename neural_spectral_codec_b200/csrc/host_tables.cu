@@ -7,7 +7,7 @@
 #include <mutex>
 #include <vector>
 
-#include "nsc_internal.h"
+#include "nsc_point.h"
 
 namespace nsc {
 
@@ -148,17 +148,26 @@ struct Memo {
 std::mutex g_mu;
 std::vector<Memo> g_memo;
 
-struct ColPoly {
-    float c[kColTerms];
-    double err;
-};
-const ColPoly& col_poly() {
-    static const ColPoly cp = [] {
-        ColPoly r;
-        r.err = fit_atan(1.0, kColTerms, 360.0 / (2.0 * 3.14159265358979323846), r.c);
-        return r;
+// Max error (radians) of the literal column polynomial of nsc_point.h, evaluated as the
+// kernel evaluates it (float32 Horner with FMA).
+double col_poly_error() {
+    static const double err = [] {
+        const float c[kColTerms] = {NSC_COL_C0, NSC_COL_C1, NSC_COL_C2, NSC_COL_C3,
+                                    NSC_COL_C4, NSC_COL_C5, NSC_COL_C6};
+        const double scale = 360.0 / (2.0 * 3.14159265358979323846);
+        double worst = 0;
+        const int grid = 400000;
+        for (int i = 0; i <= grid; ++i) {
+            const float t = (float)((double)i / grid);
+            const float t2 = t * t;
+            float p = c[kColTerms - 1];
+            for (int j = kColTerms - 2; j >= 0; --j) p = fmaf(p, t2, c[j]);
+            const float r = p * t;
+            worst = fmax(worst, fabs((double)r / scale - atan((double)t)));
+        }
+        return worst;
     }();
-    return cp;
+    return err;
 }
 
 }  // namespace
@@ -191,9 +200,7 @@ int make_device_params(const nsc_params* p, const int32_t* h_lut, DeviceParams* 
     d.eps = p->epsilon;
     d.uniform = 1.0f / (float)(d.T * d.n_bins);
 
-    const ColPoly& cp = col_poly();
-    if (!(cp.err < 1e-6)) return NSC_ERR_BAD_PARAMS;
-    memcpy(d.col_c, cp.c, sizeof(d.col_c));
+    if (!(col_poly_error() < 1e-6)) return NSC_ERR_BAD_PARAMS;
 
     // Rows. Edges are el_min + k * width, k = 0..E (range_image.py:186-188, float64).
     const double width = (p->el_max_rad - p->el_min_rad) / d.E;

@@ -266,11 +266,11 @@ int nsc_test_host_classify(const float* h_points, int point_stride, int64_t n_po
     if (n_points && (!h_points || !h_row || !h_col || !h_keep)) return NSC_ERR_NULL_POINTER;
     for (int64_t i = 0; i < n_points; ++i) {
         const float* q = h_points + i * point_stride;
-        uint32_t pix = 0, sb = 0;
-        const bool keep = classify(q[0], q[1], q[2], dp, dp.row_mode, pix, sb);
+        uint32_t row_b = 0, col_b = 0;
+        const bool keep = classify(q[0], q[1], q[2], dp, dp.row_mode, row_b, col_b) != 0xffffffffu;
         h_keep[i] = keep ? 1 : 0;
-        h_row[i] = keep ? (int32_t)(pix / kPitch) : -1;
-        int32_t c = keep ? (int32_t)(pix % kPitch) : -1;
+        h_row[i] = keep ? (int32_t)(row_b - kFloorBias) : -1;
+        int32_t c = keep ? (int32_t)(col_b - kFloorBias) : -1;
         h_col[i] = c == kAz ? 0 : c;
     }
     return NSC_OK;

@@ -15,7 +15,6 @@ namespace nsc {
 namespace {
 
 constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread (LDG feed)
-constexpr int kDefaultFeed = 0;   // kFeedLdg until the TMA ring is measured faster
 
 struct EncodeArgs {
     const float* points;
@@ -29,74 +28,82 @@ struct EncodeArgs {
     PeerOut peers;
 };
 
-__device__ __forceinline__ void scatter_min(uint32_t* img, bool keep, uint32_t pix, uint32_t sbits) {
-    // A plain read first: after the first few hits most points are not a new minimum, and a
-    // stale read can only cause a redundant atomic, never a missed one.
-    if (keep && sbits < img[pix]) atomicMin(img + pix, sbits);
+// How the point pass is fed from HBM.
+//   kFeedCpAsync  per-thread ring of 16-byte cp.async copies (SASS LDGSTS): kCpDepth-1 stages in
+//                 flight per thread without holding registers; needs 16-byte points.
+//   kFeedLdg      plain vector loads into registers (3-float points; A/B with NSC_FEED=ldg).
+// A per-warp TMA bulk-copy ring (1.5 KB cp.async.bulk per stage) was measured at 0.47 of the
+// HBM roofline against 0.81 / 0.83 for these two (profiles/r1b_ncu_full_tma.txt) and removed.
+enum Feed { kFeedLdg = 0, kFeedCpAsync = 2 };
+constexpr int kDefaultFeed = kFeedCpAsync;
+__host__ __device__ constexpr int ring_bytes_of(int feed) {
+    return feed == kFeedCpAsync ? kCpRingBytes : 0;
 }
 
-enum Feed { kFeedLdg = 0, kFeedTma = 1 };
-
-// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+// 16-byte asynchronous global -> shared copy (SASS LDGSTS), L2-only caching.
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+__device__ __forceinline__ void cp_async_commit() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr)
                  : "memory");
+    return v;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+
+// Per-pixel min of the key (bits of s). img_biased = shared address of the image minus the
+// floor bias of row and column (nsc_point.h), so the address is two integer ops. A plain read
+// first: after the first few hits most points are not a new minimum, and a stale read can only
+// cause a redundant atomic, never a missed one. No branch: the atomic is predicated.
+__device__ __forceinline__ void scatter_min(uint32_t img_biased, uint32_t row_b, uint32_t col_b,
+                                            uint32_t key) {
+    const uint32_t addr = row_b * (uint32_t)(kPitch * 4) + (col_b * 4u + img_biased);
+    uint32_t cur;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(addr));
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// global -> shared bulk copy (SASS UBLKCP), completion counted in bytes on an mbarrier.
-__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes,
-                                              uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        "setp.lt.u32 p, %1, %2;\n"
+        "@p red.shared.min.u32 [%0], %1;\n"
+        "}\n" ::"r"(addr), "r"(key), "r"(cur)
         : "memory");
 }
 
+template <int ROWMODE>
+__device__ __forceinline__ void project_point(float x, float y, float z, const DeviceParams& dp,
+                                              uint32_t img_biased, bool in_range = true) {
+    uint32_t row_b, col_b;
+    uint32_t key = classify(x, y, z, dp, ROWMODE, row_b, col_b);
+    if (!in_range) key = 0xffffffffu;
+    scatter_min(img_biased, row_b, col_b, key);
+}
+
 template <int STRIDE, int ROWMODE, int FEED>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int s_scan;
-    const SmemLayout L(dp.E, dp.T, dp.n_bins, FEED == kFeedTma);
+    const SmemLayout L(dp.E, dp.T, dp.n_bins, ring_bytes_of(FEED));
     const TailSmem S(smem_raw, L);
     uint32_t* img = reinterpret_cast<uint32_t*>(S.img);
+    const uint32_t img_biased = smem_u32(img) - kFloorBias * (uint32_t)(kPitch * 4 + 4);
     const int tid = threadIdx.x;
     const int n_pix = dp.E * kPitch;
     const int D = dp.T * dp.n_bins;
 
     init_twiddles(S.tw);
-
-    // TMA feed: every warp owns kStages x kStageBytes of the ring and one mbarrier per stage.
-    const int warp = tid >> 5, lane = tid & 31;
-    const uint32_t ring0 = smem_u32(smem_raw + L.ring_off) + warp * (kStages * kStageBytes);
-    const uint32_t bar0 = smem_u32(smem_raw + L.bar_off) + warp * (kStages * 8);
-    const float4* ring_w = reinterpret_cast<const float4*>(smem_raw + L.ring_off) +
-                           warp * (kStages * kStagePts);
-    uint32_t g_issue = 0, g_cons = 0;   // chunks issued / consumed by this warp since launch
-    if (FEED == kFeedTma) {
-        if (lane == 0) {
-#pragma unroll
-            for (int s = 0; s < kStages; ++s) mbar_init(bar0 + 8 * s, 1);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-    }
 
     for (;;) {
         __syncthreads();
@@ -109,50 +116,64 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
         const long long beg = a.offsets[scan] - a.origin;
         const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
 
-        if (FEED == kFeedTma) {
-            // Chunk c of the scan (kStagePts points) belongs to warp c % kWarps. Each warp keeps
-            // kStages bulk copies in flight into its own ring; lane 0 arms the stage's mbarrier
-            // with the byte count and issues the copy, all lanes wait on the phase parity.
-            const float4* p4 = reinterpret_cast<const float4*>(a.points) + beg;
-            const int n_chunks = (n + kStagePts - 1) / kStagePts;
-            const int mine = n_chunks > warp ? (n_chunks - warp + kWarps - 1) / kWarps : 0;
-            // The ring doubles as FFT scratch in the tail: order those generic-proxy writes
-            // before the async-proxy writes of the copies issued below.
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            auto issue = [&](int j) {
-                const int c = warp + j * kWarps;
-                const int pts = min(kStagePts, n - c * kStagePts);
-                const uint32_t slot = g_issue % kStages;
-                if (lane == 0) {
-                    mbar_expect_tx(bar0 + 8 * slot, (uint32_t)pts * 16u);
-                    bulk_copy_g2s(ring0 + slot * kStageBytes, p4 + (long long)c * kStagePts,
-                                  (uint32_t)pts * 16u, bar0 + 8 * slot);
+        if (FEED == kFeedCpAsync) {
+            // Each thread streams its own points through a private kCpDepth-deep shared-memory
+            // ring of 16-byte cp.async copies. No cross-thread barrier is needed: a thread only
+            // reads what it copied itself. Stage `it` holds points it*kStagePoints +
+            // u*kThreads + tid, u < kCpPts; stage it + kCpDepth - 1 is issued before stage it
+            // is consumed.
+            constexpr int kStagePoints = kCpPts * kThreads;
+            constexpr int kSlotBytes = kCpPts * kThreads * 16;
+            const float4* gp = reinterpret_cast<const float4*>(a.points) + beg + tid;
+            const uint32_t ring_t = smem_u32(smem_raw + L.ring_off) + tid * 16;
+            const int n_full = n / kStagePoints;              // stages with every point in range
+            const int n_iter = (n + kStagePoints - 1) / kStagePoints;
+            auto issue_checked = [&](int it) {
+                if (it < n_iter) {
+#pragma unroll
+                    for (int u = 0; u < kCpPts; ++u) {
+                        const int i = it * kStagePoints + u * kThreads;
+                        if (i + tid < n)
+                            cp_async16(ring_t + (it % kCpDepth) * kSlotBytes + u * (kThreads * 16), gp + i);
+                    }
                 }
-                ++g_issue;
+                cp_async_commit();
             };
-            int issued = 0;
-            for (; issued < mine && issued < kStages; ++issued) issue(issued);
-            for (int j = 0; j < mine; ++j) {
-                const uint32_t slot = g_cons % kStages, parity = (g_cons / kStages) & 1u;
-                mbar_wait(bar0 + 8 * slot, parity);
-                ++g_cons;
-                const int c = warp + j * kWarps;
-                const int valid = min(kStagePts, n - c * kStagePts);
-                const float4* st = ring_w + slot * kStagePts + 3 * lane;
-                const float4 v0 = st[0], v1 = st[1], v2 = st[2];
-                uint32_t p0, p1, p2, s0, s1, s2;
-                bool k0 = classify(v0.x, v0.y, v0.z, dp, ROWMODE, p0, s0) && (3 * lane + 0 < valid);
-                bool k1 = classify(v1.x, v1.y, v1.z, dp, ROWMODE, p1, s1) && (3 * lane + 1 < valid);
-                bool k2 = classify(v2.x, v2.y, v2.z, dp, ROWMODE, p2, s2) && (3 * lane + 2 < valid);
-                // consecutive points of a spinning sensor mostly share a pixel: fold them first
-                if (k0 && k1 && p0 == p1) { s1 = min(s0, s1); k0 = false; }
-                if (k1 && k2 && p1 == p2) { s2 = min(s1, s2); k1 = false; }
-                scatter_min(img, k0, p0, s0);
-                scatter_min(img, k1, p1, s1);
-                scatter_min(img, k2, p2, s2);
-                __syncwarp();   // every lane has read the stage before it is refilled
-                if (issued < mine) issue(issued++);
+#pragma unroll
+            for (int d = 0; d < kCpDepth - 1; ++d) issue_checked(d);
+            int it = 0;
+            // Main trips: kCpDepth stages per trip so every ring slot is a compile-time offset and
+            // no bounds checks remain (all stages touched are full).
+            for (; it + 2 * kCpDepth - 2 < n_full; it += kCpDepth) {
+                const float4* g = gp + (long long)it * kStagePoints;
+#pragma unroll
+                for (int s = 0; s < kCpDepth; ++s) {
+#pragma unroll
+                    for (int u = 0; u < kCpPts; ++u)
+                        cp_async16(ring_t + ((s + kCpDepth - 1) % kCpDepth) * kSlotBytes + u * (kThreads * 16),
+                                   g + (s + kCpDepth - 1) * kStagePoints + u * kThreads);
+                    cp_async_commit();
+                    cp_async_wait<kCpDepth - 1>();
+                    float4 v[kCpPts];
+#pragma unroll
+                    for (int u = 0; u < kCpPts; ++u) v[u] = lds128(ring_t + s * kSlotBytes + u * (kThreads * 16));
+#pragma unroll
+                    for (int u = 0; u < kCpPts; ++u)
+                        project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+                }
             }
+            // Remaining stages (the last few full ones and the partial one), bounds-checked.
+            for (; it < n_iter; ++it) {
+                issue_checked(it + kCpDepth - 1);
+                cp_async_wait<kCpDepth - 1>();
+#pragma unroll
+                for (int u = 0; u < kCpPts; ++u) {
+                    const int i = it * kStagePoints + u * kThreads + tid;
+                    const float4 v = lds128(ring_t + (it % kCpDepth) * kSlotBytes + u * (kThreads * 16));
+                    project_point<ROWMODE>(v.x, v.y, v.z, dp, img_biased, i < n);
+                }
+            }
+            cp_async_wait<0>();
         } else if (STRIDE == 4) {
             const float4* p4 = reinterpret_cast<const float4*>(a.points) + beg;
             for (int base = 0; base < n; base += kThreads * kUnroll) {
@@ -163,11 +184,8 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
                     v[u] = i < n ? __ldcs(p4 + i) : make_float4(NAN, NAN, NAN, 0.0f);
                 }
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    uint32_t pix, sb;
-                    const bool keep = classify(v[u].x, v[u].y, v[u].z, dp, ROWMODE, pix, sb);
-                    scatter_min(img, keep, pix, sb);
-                }
+                for (int u = 0; u < kUnroll; ++u)
+                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
             }
         } else {
             const float* p = a.points + beg * 3;
@@ -182,11 +200,8 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
                     z[u] = in ? __ldcs(p + 3 * (long long)i + 2) : NAN;
                 }
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    uint32_t pix, sb;
-                    const bool keep = classify(x[u], y[u], z[u], dp, ROWMODE, pix, sb);
-                    scatter_min(img, keep, pix, sb);
-                }
+                for (int u = 0; u < kUnroll; ++u)
+                    project_point<ROWMODE>(x[u], y[u], z[u], dp, img_biased);
             }
         }
         __syncthreads();
@@ -222,10 +237,10 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
 
 // Range images in, descriptors out: SpectralEncoder.forward / encode_range_image
 // (spectral_encoder.py:160-204, :231-261). No projection, no interpolation.
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 encode_images_kernel(const float* __restrict__ images, int n_images, int rows,
                      const __grid_constant__ DeviceParams dp, float* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const SmemLayout L(rows, dp.T, dp.n_bins);
     const TailSmem S(smem_raw, L);
     const int D = dp.T * dp.n_bins;
@@ -248,9 +263,9 @@ encode_images_kernel(const float* __restrict__ images, int n_images, int rows,
 }
 
 // interpolate_range_image on device images (range_image.py:15-89).
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kMinBlocks)
 interpolate_kernel(const float* __restrict__ in, int n_images, int rows, float* __restrict__ out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const SmemLayout L(rows, 1, 1);
     const TailSmem S(smem_raw, L);
     for (int im = blockIdx.x; im < n_images; im += gridDim.x) {
@@ -335,21 +350,19 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     a.peers.row0 = peer_row0;
     for (int i = 0; i < NSC_MAX_PEERS; ++i) a.peers.ptr[i] = i < n_peers ? d_peer_out[i] : nullptr;
 
-    // Feed of the point pass: per-warp TMA bulk-copy ring (4-float points) or plain vector
-    // loads (3-float points are not 16-byte granular). NSC_FEED=ldg|tma overrides for A/B runs.
+    // Feed of the point pass (see enum Feed). NSC_FEED=ldg|cpasync overrides for A/B runs.
     static const int feed_override = [] {
         const char* e = getenv("NSC_FEED");
         if (!e) return -1;
-        return strcmp(e, "tma") == 0 ? (int)kFeedTma : strcmp(e, "ldg") == 0 ? (int)kFeedLdg : -1;
+        return strcmp(e, "ldg") == 0 ? (int)kFeedLdg : strcmp(e, "cpasync") == 0 ? (int)kFeedCpAsync : -1;
     }();
-    int feed = kDefaultFeed;
-    if (feed_override >= 0) feed = feed_override;
+    int feed = feed_override >= 0 ? feed_override : kDefaultFeed;
     if (stride != 4) feed = kFeedLdg;
-    const SmemLayout L(dp.E, dp.T, dp.n_bins, feed == kFeedTma);
+    const SmemLayout L(dp.E, dp.T, dp.n_bins, ring_bytes_of(feed));
     void (*kernel)(const EncodeArgs, const DeviceParams) = nullptr;
-    if (feed == kFeedTma) {
-        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedTma>
-                                         : encode_points_kernel<4, kRowSearch, kFeedTma>;
+    if (feed == kFeedCpAsync) {
+        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedCpAsync>
+                                         : encode_points_kernel<4, kRowSearch, kFeedCpAsync>;
     } else if (stride == 4) {
         kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedLdg>
                                          : encode_points_kernel<4, kRowSearch, kFeedLdg>;

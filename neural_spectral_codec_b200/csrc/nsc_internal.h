@@ -29,7 +29,6 @@ struct DeviceParams {
     float s_lo, s_hi;      // keep a point iff s_lo <= (x*x + y*y) + z*z <= s_hi (host_tables.cu)
     float eps;
     float uniform;         // 1 / (T * n_bins) in float32
-    float col_c[kColTerms];   // atan(t) * 360/(2 pi) = t * P(t^2), t in [0,1]
     float row_p[kRowTerms];   // (atan(u) - el_min) / row_width = row_off + u * P(u^2)
     float row_off;
     float u_lo, u_hi;      // clamp of u = z / rho that keeps the row value inside (0, E)

@@ -32,6 +32,21 @@
 
 namespace nsc {
 
+// atan(t) * 360 / (2 pi) = t * P(t^2) on [0, 1]: near-minimax fit (host_tables.cu fit_atan(1, 7)),
+// max error 3.1e-7 rad in float32 Horner/FMA arithmetic, re-verified at library init. Literal
+// constants so that every FFMA of the chain takes its coefficient as an immediate.
+#define NSC_COL_C0 5.729555511e+01f
+#define NSC_COL_C1 -1.908944511e+01f
+#define NSC_COL_C2 1.134904289e+01f
+#define NSC_COL_C3 -7.582146645e+00f
+#define NSC_COL_C4 4.562099934e+00f
+#define NSC_COL_C5 -1.925379395e+00f
+#define NSC_COL_C6 3.902867138e-01f
+
+// The device keeps floor() results as the raw bits of (v + 2^23) rounded down: the integer sits
+// in the low mantissa bits above this bias, and the bias is folded into the address constant.
+constexpr uint32_t kFloorBias = 0x4B000000u;
+
 // float32 multiply / add with exactly one rounding each (no FMA contraction).
 NSC_HD float mul_rn(float a, float b) {
 #if defined(__CUDA_ARCH__)
@@ -78,45 +93,50 @@ NSC_HD uint32_t f2u(float a) {
 #endif
 }
 
-
-// floor of a float in [0, 2^22) as an integer, without the conversion pipe: adding 2^23 with
-// round-down leaves the integer part in the low mantissa bits.
-NSC_HD uint32_t floor_bits(float v) {
+// floor(v + add) for v + add in [0, 2^22), plus kFloorBias (see above). On the device one FADD
+// with round-down of the exact sum v + (add + 2^23); add must be an integer.
+NSC_HD uint32_t floor_biased(float v, float add) {
 #if defined(__CUDA_ARCH__)
-    return __float_as_uint(__fadd_rd(v, 8388608.0f)) - 0x4B000000u;
+    return __float_as_uint(__fadd_rd(v, add + 8388608.0f));
 #else
-    return (uint32_t)floorf(v);
+    return (uint32_t)floor((double)v + (double)add) + kFloorBias;
 #endif
 }
 
-// Column in [0, 360]; 360 only for azimuth == 2*pi exactly, which the reference wraps to 0.
-template <typename P>
-NSC_HD uint32_t column_of(float x, float y, const P& dp) {
+// Column + kFloorBias, column in [0, 360]; 360 only for azimuth == 2*pi exactly, which the
+// reference wraps to 0 (the kernels keep a 361st column and fold it).
+NSC_HD uint32_t column_biased(float x, float y) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(fmaxf(ax, ay), 1e-30f);
     const float mn = fminf(ax, ay);
     const float t = mn * rcp_fast(mx);
     const float t2 = t * t;
-    float p = dp.col_c[kColTerms - 1];
-#pragma unroll
-    for (int i = kColTerms - 2; i >= 0; --i) p = fmaf(p, t2, dp.col_c[i]);
+    float p = NSC_COL_C6;
+    p = fmaf(p, t2, NSC_COL_C5);
+    p = fmaf(p, t2, NSC_COL_C4);
+    p = fmaf(p, t2, NSC_COL_C3);
+    p = fmaf(p, t2, NSC_COL_C2);
+    p = fmaf(p, t2, NSC_COL_C1);
+    p = fmaf(p, t2, NSC_COL_C0);
     float r = p * t;                                  // [0, 45] column units
     if (ay > ax) r = 90.0f - r;                       // |y| > |x|: reflect about the bisector
-    if ((int32_t)f2u(x) < 0) r = 180.0f - r;      // sign BIT of x: atan2(+-0, -0) = +-pi
+    if ((int32_t)f2u(x) < 0) r = 180.0f - r;          // sign BIT of x: atan2(+-0, -0) = +-pi
     r = copysignf(r, y);                              // sign bit of y
-    return floor_bits(r + 180.0f);
+    r = fminf(r, 180.0f);                             // NaN (x and y both non-finite) -> in range
+    return floor_biased(r, 180.0f);
 }
 
+// Row + kFloorBias.
 template <typename P>
-NSC_HD uint32_t row_of(float z, float rho2, const P& dp, int row_mode) {
+NSC_HD uint32_t row_biased(float z, float rho2, const P& dp, int row_mode) {
     if (row_mode == kRowPoly) {
-        float u = z * rsqrt_fast(rho2);                // rho2 == 0 -> +-inf, clamped below
-        u = fminf(fmaxf(u, dp.u_lo), dp.u_hi);
+        float u = z * rsqrt_fast(rho2);               // rho2 == 0 -> +-inf, clamped below
+        u = fminf(fmaxf(u, dp.u_lo), dp.u_hi);        // also maps NaN into the field of view
         const float u2 = u * u;
         float p = dp.row_p[kRowTerms - 1];
 #pragma unroll
         for (int i = kRowTerms - 2; i >= 0; --i) p = fmaf(p, u2, dp.row_p[i]);
-        return floor_bits(fmaf(p, u, dp.row_off));    // in (0, E) by construction of u_lo/u_hi
+        return floor_biased(fmaf(p, u, dp.row_off), 0.0f);   // in (0, E) by construction of u_lo/u_hi
     }
     const float q = z * fabsf(z);
     int row = 0;
@@ -125,22 +145,21 @@ NSC_HD uint32_t row_of(float z, float rho2, const P& dp, int row_mode) {
         const int k = row + step;
         if (k < dp.E && q >= dp.row_c[k] * rho2) row = k;
     }
-    return (uint32_t)row;
+    return (uint32_t)row + kFloorBias;
 }
 
-// One point -> (keep, pixel index into the kPitch-wide min image, bits of s).
+// One point -> biased row and column (always inside the kPitch-wide image, whatever the input)
+// and the scatter key: the bits of s for a kept point, 0xffffffff (never a minimum) otherwise.
 template <typename P>
-NSC_HD bool classify(float x, float y, float z, const P& dp, int row_mode, uint32_t& pix,
-                     uint32_t& sbits) {
+NSC_HD uint32_t classify(float x, float y, float z, const P& dp, int row_mode, uint32_t& row_b,
+                         uint32_t& col_b) {
     const float xx = mul_rn(x, x), yy = mul_rn(y, y), zz = mul_rn(z, z);
     const float rho2 = add_rn(xx, yy);
     const float s = add_rn(rho2, zz);
     const bool keep = (s >= dp.s_lo) && (s <= dp.s_hi);   // false for NaN / Inf
-    const uint32_t col = column_of(x, y, dp);
-    const uint32_t row = row_of(z, rho2, dp, row_mode);
-    pix = row * (uint32_t)kPitch + col;
-    sbits = f2u(s);
-    return keep;
+    col_b = column_biased(x, y);
+    row_b = row_biased(z, rho2, dp, row_mode);
+    return keep ? f2u(s) : 0xffffffffu;
 }
 
 }  // namespace nsc

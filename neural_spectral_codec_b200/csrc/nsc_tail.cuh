@@ -5,42 +5,53 @@
 //   contiguous-frequency bin sums (:118-158) -> L1 normalisation (:197-202).
 // All functions are CTA-collective: every thread of the block must call them.
 #pragma once
+#include "nsc_fft.cuh"
 #include "nsc_internal.h"
 
 namespace nsc {
 
-constexpr int kThreads = 512;
+#ifndef NSC_THREADS
+#define NSC_THREADS 512
+#endif
+#ifndef NSC_MIN_BLOCKS
+#define NSC_MIN_BLOCKS 2
+#endif
+constexpr int kThreads = NSC_THREADS;
 constexpr int kWarps = kThreads / 32;
+constexpr int kMinBlocks = NSC_MIN_BLOCKS;   // resident CTAs per SM the kernels are compiled for
 
-// Per-warp bulk-copy ring of the point pass (TMA feed): kStages stages of kStagePts points.
-constexpr int kStagePts = 96;            // 3 consecutive points per lane: 48-byte lane stride is
-                                         // conflict-free for 16-byte shared loads
-constexpr int kStages = 3;
-constexpr int kStageBytes = kStagePts * 16;
-constexpr int kRingBytes = kWarps * kStages * kStageBytes;   // 73 728 B per CTA
+// Per-thread cp.async ring (LDGSTS feed): kCpDepth stages of kCpPts 16-byte points per thread.
+#ifndef NSC_CP_PTS
+#define NSC_CP_PTS 2
+#endif
+#ifndef NSC_CP_DEPTH
+#define NSC_CP_DEPTH 4
+#endif
+constexpr int kCpPts = NSC_CP_PTS;
+constexpr int kCpDepth = NSC_CP_DEPTH;
+constexpr int kCpRingBytes = kCpDepth * kCpPts * kThreads * 16;   // 65 536 B per CTA
 
 // Shared-memory carve-up, identical on host (size) and device (pointers). With a ring the two
 // FFT buffers alias it: the ring is idle (fully consumed) while the tail runs.
 struct SmemLayout {
     int img_off, tw_off, fa_off, fb_off, hist_off, mask_off, nvalid_off, src_off, red_off;
-    int ring_off, bar_off, total;
+    int ring_off, total;
     int n_sig;  // complex FFTs per batch
-    __host__ __device__ SmemLayout(int rows, int T, int n_bins, bool ring = false) {
+    __host__ __device__ SmemLayout(int rows, int T, int n_bins, int ring_bytes = 0) {
+        const bool ring = ring_bytes > 0;
         int o = 0;
         auto take = [&o](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
         n_sig = (T + 1) / 2 < kMaxSignals ? (T + 1) / 2 : kMaxSignals;
         img_off = take(rows * kPitch * 4);
         tw_off = take(kAz * 8);
-        if (ring) {
-            ring_off = take(kRingBytes);
-            fa_off = ring_off;
-            fb_off = ring_off + n_sig * kAz * 8;      // 2 * 8 * 2880 = 46 080 <= kRingBytes
-            bar_off = take(kWarps * kStages * 8);
-        } else {
-            ring_off = bar_off = 0;
-            fa_off = take(n_sig * kAz * 8);
-            fb_off = take(n_sig * kAz * 8);
-        }
+        // The second FFT buffer may reuse the image: once the (single) batch of signals has been
+        // loaded from the image into fa, the image is dead.
+        const int sig_bytes = n_sig * kAz * 8;
+        const bool fb_on_img = (T + 1) / 2 <= kMaxSignals && rows * kPitch * 4 >= sig_bytes;
+        const int scratch = fb_on_img ? sig_bytes : 2 * sig_bytes;
+        ring_off = take(ring && ring_bytes > scratch ? ring_bytes : scratch);
+        fa_off = ring_off;
+        fb_off = fb_on_img ? img_off : ring_off + sig_bytes;
         hist_off = take(T * n_bins * 4);
         mask_off = take(rows * kMaskWords * 4);
         nvalid_off = take(rows * 4);
@@ -166,36 +177,15 @@ __device__ __forceinline__ float pooled_value(const TailSmem& S, int rows, int T
     return sum / (float)(r1 - r0);
 }
 
-// One Stockham pass of radix R over n_sig complex signals of length 360: output element o of
-// every butterfly is a direct R-term sum with twiddles looked up in tw[] (index arithmetic
-// mod 360), one thread per output element.
+// One Stockham pass of radix R over n_sig complex signals of length 360: one thread per
+// butterfly (nsc_fft.cuh), R inputs and outputs in registers.
 template <int R, int NS>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ x, float2* __restrict__ y,
                                          const float2* __restrict__ tw, int n_sig) {
-    constexpr int kStrideIn = kAz / R;
-    constexpr int kS1 = kAz / (NS * R), kS2 = kAz / R;
-    for (int t = threadIdx.x; t < n_sig * kAz; t += kThreads) {
-        const int g = t / kAz, o = t - g * kAz;
-        const int blk = o / (NS * R), rem = o - blk * (NS * R);
-        const int q = rem / NS, k = rem - q * NS;
-        const int j = blk * NS + k;
-        int step = k * kS1 + q * kS2;
-        step -= (step >= kAz) ? kAz : 0;   // k*kS1 < 360/R, q*kS2 < 360: one wrap at most
-        const float2* xin = x + g * kAz + j;
-        float re = 0.0f, im = 0.0f;
-        int idx = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const float2 v = xin[r * kStrideIn];
-            const float2 w = tw[idx];
-            re = fmaf(v.x, w.x, re);
-            re = fmaf(-v.y, w.y, re);
-            im = fmaf(v.x, w.y, im);
-            im = fmaf(v.y, w.x, im);
-            idx += step;
-            idx -= (idx >= kAz) ? kAz : 0;
-        }
-        y[g * kAz + o] = make_float2(re, im);
+    constexpr int kBfly = kAz / R;
+    for (int t = threadIdx.x; t < n_sig * kBfly; t += kThreads) {
+        const int g = t / kBfly, j = t - g * kBfly;
+        stockham_butterfly<R, NS>(x + g * kAz, y + g * kAz, tw, j);
     }
 }
 
