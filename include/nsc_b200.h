@@ -163,6 +163,35 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
                         const int64_t* h_offsets, int n_scans, const nsc_params* p,
                         const int32_t* h_lut, float* h_out);
 
+/* ---- stage-1 retrieval over the descriptor database (first "next" row) ---- */
+/* Normalised CDF rows of a block of database histograms: cdf = cumsum(h / (sum h + eps)) where
+ * sum h > eps, cumsum(h) otherwise -- the database half of wasserstein_distance_batch_torch
+ * (reference src/retrieval/wasserstein.py:157-166), computed once when rows are inserted
+ * (WassersteinRetriever.add_to_database, :300-326) instead of on every query.
+ * d_hists, d_cdfs: float32[n_rows * n_bins]; n_bins <= 1024. */
+int nsc_wasserstein_cdf(const float* d_hists, int64_t n_rows, int n_bins, float epsilon,
+                        float* d_cdfs, void* stream);
+
+/* Replaces WassersteinRetriever.query (wasserstein.py:328-367) for n_queries queries at once,
+ * with the spatial exclusion of TwoStageRetrieval._global_retrieval
+ * (src/retrieval/two_stage_retrieval.py:158-166) folded in.
+ *   d_query_hists  float32[n_queries * n_bins] raw query histograms (normalised in-kernel:
+ *                  h / sum h where sum h > eps, wasserstein.py:152-154)
+ *   d_db_cdfs      float32[n_db * n_bins] from nsc_wasserstein_cdf
+ *   d_db_xyz, d_query_xyz  float64 positions (pose[:3, 3]); both NULL = no spatial filter;
+ *                  database rows closer than min_spatial_distance (strict <) get distance +inf
+ *   d_distances    float32[n_queries * n_db] OUT: sum_i |cdf_db[i] - cdf_q[i]| (also scratch
+ *                  for the selection; always written)
+ *   top_k          0 = distances only; else <= 1024: d_top_idx int64[n_queries * top_k] (-1
+ *                  padded), d_top_dist float32 (ascending, +inf padded), d_top_count
+ *                  int32[n_queries] = min(top_k, rows not excluded). Ties are broken by the
+ *                  lower database index (deterministic). */
+int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float* d_db_cdfs,
+                          int64_t n_db, int n_bins, float epsilon, const double* d_db_xyz,
+                          const double* d_query_xyz, double min_spatial_distance,
+                          float* d_distances, int top_k, int64_t* d_top_idx, float* d_top_dist,
+                          int32_t* d_top_count, void* stream);
+
 /* ---- test hooks (not part of the product path) ----------------------------------------- */
 /* Evaluates the kernel's per-point inline function (csrc/nsc_point.h) on the HOST for
  * n_points points: row / col (or -1) and keep flag per point. It exists so that the CPU-only

@@ -1,0 +1,377 @@
+// Stage-1 retrieval over the descriptor database: 1-D Wasserstein
+// distance = sum |CDF_db - CDF_query| (reference src/retrieval/wasserstein.py:134-172), the
+// spatial exclusion of src/retrieval/two_stage_retrieval.py:158-166 and the top-K of
+// wasserstein.py:358-364, as three kernels:
+//   cdf_rows_kernel        histogram rows -> normalised CDF rows, once per database insert
+//   wasserstein_kernel     streams the CDF rows once per group of <= kMaxQueries queries (HBM bound:
+//                          4*n_bins bytes per row), writes the (Q, N) distances, +inf where excluded
+//   topk_kernel            per query: 4-pass radix select of the k-th smallest distance, ordered
+//                          gather, bitonic sort of the k winners by (distance, index)
+#include <math.h>
+
+#include "nsc_internal.h"
+
+namespace nsc {
+
+namespace {
+
+constexpr int kRThreads = 256;
+constexpr int kRWarps = kRThreads / 32;
+constexpr int kMaxQueries = 8;      // query CDFs resident in shared memory per launch
+constexpr int kMaxPerLane = 32;     // n_bins <= 1024
+constexpr int kTopThreads = 1024;
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// A warp turns one histogram row, staged in shared memory, into its normalised CDF held in
+// registers: lane l owns the contiguous elements [l*per, (l+1)*per). mode 0: database row,
+// h / (sum + eps) if sum > eps else h (wasserstein.py:157-162); mode 1: query, h / sum if
+// sum > eps (wasserstein.py:152-154).
+template <int MODE>
+__device__ __forceinline__ void row_cdf(const float* row_s, int n_bins, int per, float eps, int lane,
+                                        float* c /* kMaxPerLane */) {
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        const int e = lane * per + i;
+        c[i] = (i < per && e < n_bins) ? row_s[e] : 0.0f;
+        s += c[i];
+    }
+    const float total = warp_sum(s);
+    const bool norm = total > eps;
+    const float denom = MODE == 0 ? total + eps : total;
+    float run = 0.0f;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i) {
+        if (i < per) {
+            const float h = norm ? __fdiv_rn(c[i], denom) : c[i];
+            run += h;
+            c[i] = run;
+        }
+    }
+    // exclusive scan of the lane totals
+    float incl = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    const float offset = incl - run;
+#pragma unroll
+    for (int i = 0; i < kMaxPerLane; ++i)
+        if (i < per) c[i] += offset;
+}
+
+__global__ void __launch_bounds__(kRThreads)
+cdf_rows_kernel(const float* __restrict__ hists, long long n, int n_bins, float eps,
+                float* __restrict__ cdfs) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (n_bins + 31) / 32;
+    float* row_s = smem + warp * (per * 32);
+    const long long n_warps = (long long)gridDim.x * kRWarps;
+    for (long long r = (long long)blockIdx.x * kRWarps + warp; r < n; r += n_warps) {
+        const float* src = hists + r * n_bins;
+        for (int e = lane; e < per * 32; e += 32) row_s[e] = e < n_bins ? __ldcs(src + e) : 0.0f;
+        __syncwarp();
+        float c[kMaxPerLane];
+        row_cdf<0>(row_s, n_bins, per, eps, lane, c);
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i)
+            if (i < per) row_s[lane * per + i] = c[i];
+        __syncwarp();
+        float* dst = cdfs + r * n_bins;
+        for (int e = lane; e < n_bins; e += 32) dst[e] = row_s[e];
+        __syncwarp();
+    }
+}
+
+struct QueryArgs {
+    const float* queries;     // Q x n_bins histograms
+    const float* db_cdfs;     // N x n_bins
+    const double* db_xyz;     // N x 3 or null
+    const double* query_xyz;  // Q x 3 or null
+    double min_dist;
+    float* distances;         // Q x N
+    long long n_db;
+    int n_queries, n_bins;
+    float eps;
+};
+
+__global__ void __launch_bounds__(kRThreads)
+wasserstein_kernel(const __grid_constant__ QueryArgs a) {
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per = (a.n_bins + 31) / 32, padded = per * 32;
+    float* qcdf = smem;                                  // Q x padded, lane-contiguous layout
+    float* stage = smem + a.n_queries * padded;          // kRWarps x padded
+    // query CDFs (wasserstein.py:152-154,165), one warp per query
+    for (int q = warp; q < a.n_queries; q += kRWarps) {
+        float* row_s = stage + warp * padded;
+        for (int e = lane; e < padded; e += 32) row_s[e] = e < a.n_bins ? a.queries[(long long)q * a.n_bins + e] : 0.0f;
+        __syncwarp();
+        float c[kMaxPerLane];
+        row_cdf<1>(row_s, a.n_bins, per, a.eps, lane, c);
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i)
+            if (i < per) qcdf[q * padded + lane * per + i] = c[i];
+        __syncwarp();
+    }
+    __syncthreads();
+
+    float* row_s = stage + warp * padded;
+    const long long n_warps = (long long)gridDim.x * kRWarps;
+    for (long long r = (long long)blockIdx.x * kRWarps + warp; r < a.n_db; r += n_warps) {
+        const float* src = a.db_cdfs + r * a.n_bins;
+        for (int e = lane; e < padded; e += 32) row_s[e] = e < a.n_bins ? __ldcs(src + e) : 0.0f;
+        __syncwarp();
+        float c[kMaxPerLane];
+#pragma unroll
+        for (int i = 0; i < kMaxPerLane; ++i) c[i] = i < per ? row_s[lane * per + i] : 0.0f;
+        double px = 0, py = 0, pz = 0;
+        const bool spatial = a.db_xyz != nullptr && a.query_xyz != nullptr;
+        if (spatial) { px = a.db_xyz[3 * r]; py = a.db_xyz[3 * r + 1]; pz = a.db_xyz[3 * r + 2]; }
+        for (int q = 0; q < a.n_queries; ++q) {
+            const float* qc = qcdf + q * padded + lane * per;
+            float d = 0.0f;
+#pragma unroll
+            for (int i = 0; i < kMaxPerLane; ++i)
+                if (i < per && lane * per + i < a.n_bins) d += fabsf(c[i] - qc[i]);
+            d = warp_sum(d);
+            if (lane == 0) {
+                if (spatial) {   // two_stage_retrieval.py:160-164: skip keyframes closer than the threshold
+                    const double dx = px - a.query_xyz[3 * q], dy = py - a.query_xyz[3 * q + 1],
+                                 dz = pz - a.query_xyz[3 * q + 2];
+                    if (sqrt(dx * dx + dy * dy + dz * dz) < a.min_dist) d = INFINITY;
+                }
+                a.distances[(long long)q * a.n_db + r] = d;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- top-K ----------------------------------------------------------------------------------
+struct TopkArgs {
+    const float* distances;   // Q x N, >= 0 or +inf (excluded)
+    long long n_db;
+    int k;
+    long long* top_idx;       // Q x k, -1 padded
+    float* top_dist;          // Q x k, +inf padded
+    int* top_count;           // Q
+};
+
+__device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* warp_tot, unsigned* total) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned t = warp_tot[lane];
+        unsigned ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned o = __shfl_up_sync(0xffffffffu, ti, d);
+            if (lane >= d) ti += o;
+        }
+        warp_tot[lane] = ti - t;
+        if (lane == 31) *total = ti;
+    }
+    __syncthreads();
+    const unsigned r = warp_tot[warp] + incl - v;
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kTopThreads)
+topk_kernel(const __grid_constant__ TopkArgs a) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned s_total, s_prefix, s_need, s_nvalid;
+    __shared__ unsigned long long sel[kTopThreads];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const unsigned* keys = reinterpret_cast<const unsigned*>(a.distances + (long long)q * a.n_db);
+    const unsigned kInf = 0x7f800000u;
+
+    // number of candidates (finite distances)
+    unsigned cnt = 0;
+    for (long long i = tid; i < a.n_db; i += kTopThreads) cnt += keys[i] < kInf;
+    cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
+    if (tid == 0) s_nvalid = 0;
+    __syncthreads();
+    if ((tid & 31) == 0) atomicAdd(&s_nvalid, cnt);
+    __syncthreads();
+    const unsigned k = min((unsigned)a.k, s_nvalid);
+
+    // radix select: after the loop `prefix` is the k-th smallest key and `need` how many keys
+    // equal to it are taken (those with the lowest indices).
+    unsigned prefix = 0, need = k;
+    if (k > 0) {
+        for (int shift = 24; shift >= 0; shift -= 8) {
+            if (tid < 256) hist[tid] = 0;
+            __syncthreads();
+            const unsigned mask_hi = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
+            for (long long i = tid; i < a.n_db; i += kTopThreads) {
+                const unsigned key = keys[i];
+                if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned acc = 0, b = 0;
+                for (; b < 256; ++b) {
+                    if (acc + hist[b] >= need) break;
+                    acc += hist[b];
+                }
+                s_prefix = prefix | (b << shift);
+                s_need = need - acc;
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            need = s_need;
+        }
+    }
+    // ordered gather: all keys < prefix, and the first `need` keys == prefix in index order
+    unsigned base_less = 0, base_eq = 0;
+    const unsigned n_less = k - need;
+    sel[tid] = ~0ull;
+    __syncthreads();
+    if (k > 0) {
+        for (long long i0 = 0; i0 < a.n_db; i0 += kTopThreads) {
+            const long long i = i0 + tid;
+            const unsigned key = i < a.n_db ? keys[i] : 0xffffffffu;
+            const unsigned less = key < prefix, eq = key == prefix;
+            unsigned tot_less, tot_eq;
+            const unsigned pl = block_excl_scan(less, warp_tot, &s_total);
+            tot_less = s_total;
+            __syncthreads();
+            const unsigned pe = block_excl_scan(eq, warp_tot, &s_total);
+            tot_eq = s_total;
+            __syncthreads();
+            if (less) sel[base_less + pl] = ((unsigned long long)key << 32) | (unsigned)i;
+            if (eq && base_eq + pe < need) sel[n_less + base_eq + pe] = ((unsigned long long)key << 32) | (unsigned)i;
+            base_less += tot_less;
+            base_eq += tot_eq;
+        }
+    }
+    __syncthreads();
+    // bitonic sort of kTopThreads packed (distance bits, index) keys, ascending; unused = ~0
+    for (unsigned size = 2; size <= kTopThreads; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned j = tid ^ stride;
+            if (j > (unsigned)tid) {
+                const unsigned long long x = sel[tid], y = sel[j];
+                const bool up = (tid & size) == 0;
+                if ((x > y) == up) { sel[tid] = y; sel[j] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid < a.k) {
+        const bool ok = (unsigned)tid < k;
+        a.top_idx[(long long)q * a.k + tid] = ok ? (long long)(unsigned)(sel[tid] & 0xffffffffull) : -1;
+        a.top_dist[(long long)q * a.k + tid] = ok ? __uint_as_float((unsigned)(sel[tid] >> 32)) : INFINITY;
+    }
+    if (tid == 0) a.top_count[q] = (int)k;
+}
+
+int sm_count(int* sms) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return record_cuda(e);
+    e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+    return e == cudaSuccess ? NSC_OK : record_cuda(e);
+}
+
+}  // namespace
+
+}  // namespace nsc
+
+using namespace nsc;
+
+extern "C" {
+
+int nsc_wasserstein_cdf(const float* d_hists, int64_t n_rows, int n_bins, float epsilon,
+                        float* d_cdfs, void* stream) {
+    if (n_rows < 0) return NSC_ERR_BAD_COUNT;
+    if (n_bins < 1 || n_bins > 32 * kMaxPerLane) return NSC_ERR_BAD_PARAMS;
+    if (n_rows == 0) return NSC_OK;
+    if (!d_hists || !d_cdfs) return NSC_ERR_NULL_POINTER;
+    int sms = 0;
+    int st = sm_count(&sms);
+    if (st != NSC_OK) return st;
+    const int padded = ((n_bins + 31) / 32) * 32;
+    const size_t smem = (size_t)kRWarps * padded * 4;
+    long long grid = (n_rows + kRWarps - 1) / kRWarps;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    cdf_rows_kernel<<<(int)grid, kRThreads, smem, (cudaStream_t)stream>>>(d_hists, n_rows, n_bins,
+                                                                         epsilon, d_cdfs);
+    return record_cuda(cudaGetLastError());
+}
+
+int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float* d_db_cdfs,
+                          int64_t n_db, int n_bins, float epsilon, const double* d_db_xyz,
+                          const double* d_query_xyz, double min_spatial_distance,
+                          float* d_distances, int top_k, int64_t* d_top_idx, float* d_top_dist,
+                          int32_t* d_top_count, void* stream) {
+    if (n_queries < 0 || n_db < 0 || top_k < 0) return NSC_ERR_BAD_COUNT;
+    if (n_bins < 1 || n_bins > 32 * kMaxPerLane || top_k > kTopThreads) return NSC_ERR_BAD_PARAMS;
+    if (n_db >= (1ll << 32)) return NSC_ERR_BAD_COUNT;
+    if (n_queries == 0) return NSC_OK;
+    if (!d_query_hists || !d_distances) return NSC_ERR_NULL_POINTER;
+    if (n_db > 0 && !d_db_cdfs) return NSC_ERR_NULL_POINTER;
+    if (top_k > 0 && (!d_top_idx || !d_top_dist || !d_top_count)) return NSC_ERR_NULL_POINTER;
+    if ((d_db_xyz == nullptr) != (d_query_xyz == nullptr)) return NSC_ERR_NULL_POINTER;
+    cudaStream_t s = (cudaStream_t)stream;
+    int sms = 0;
+    int st = sm_count(&sms);
+    if (st != NSC_OK) return st;
+    const int padded = ((n_bins + 31) / 32) * 32;
+    if (n_db > 0) {
+        for (int q0 = 0; q0 < n_queries; q0 += kMaxQueries) {
+            QueryArgs a;
+            a.n_queries = n_queries - q0 < kMaxQueries ? n_queries - q0 : kMaxQueries;
+            a.queries = d_query_hists + (size_t)q0 * n_bins;
+            a.db_cdfs = d_db_cdfs;
+            a.db_xyz = d_db_xyz;
+            a.query_xyz = d_query_xyz ? d_query_xyz + 3 * (size_t)q0 : nullptr;
+            a.min_dist = min_spatial_distance;
+            a.distances = d_distances + (size_t)q0 * n_db;
+            a.n_db = n_db;
+            a.n_bins = n_bins;
+            a.eps = epsilon;
+            const size_t smem = (size_t)(a.n_queries + kRWarps) * padded * 4;
+            cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return record_cuda(e);
+            long long grid = (n_db + kRWarps - 1) / kRWarps;
+            if (grid > (long long)sms * 4) grid = (long long)sms * 4;
+            wasserstein_kernel<<<(int)grid, kRThreads, smem, s>>>(a);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) return record_cuda(e);
+        }
+    }
+    if (top_k > 0) {
+        TopkArgs t;
+        t.distances = d_distances;
+        t.n_db = n_db;
+        t.k = top_k;
+        t.top_idx = (long long*)d_top_idx;
+        t.top_dist = d_top_dist;
+        t.top_count = d_top_count;
+        topk_kernel<<<n_queries, kTopThreads, 0, s>>>(t);
+        return record_cuda(cudaGetLastError());
+    }
+    return NSC_OK;
+}
+
+}  // extern "C"

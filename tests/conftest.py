@@ -8,6 +8,9 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+# golden files that hold a point cloud and the reference's outputs for it
+POINT_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
+                     if f.endswith(".npz") and not f.startswith(("forward_", "retrieval")))
 
 
 def pytest_configure(config):

@@ -14,15 +14,13 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_DIR
+from conftest import GOLDEN_DIR, POINT_CASES
 from oracle import nsc_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
 RTOL, ATOL, L2REL = 1e-4, 1e-7, 1e-5
 
-POINT_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))
-                     if not os.path.basename(p).startswith("forward_"))
 CTOR = {"elev64_pooled": dict(n_elevation=64), "elev64_sparse": dict(n_elevation=64),
         "no_interp": dict(interpolate_empty=False)}
 

@@ -1,0 +1,125 @@
+"""CUDA stage-1 retrieval against the reference's recorded outputs and the oracle.
+
+Tolerances: a distance is a float32 sum of 800 |CDF differences| of float32 prefix sums; the
+GPU's summation order differs from the CPU's, and the reference's own torch and numpy paths
+differ by up to 2e-3 absolute on the recorded vectors. rtol 2e-5 / atol 1e-4 (distances range
+over [0, 800)); indices must be identical wherever the oracle's neighbouring distances differ
+by more than that tolerance (exact ties / near ties may swap).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle import retrieval_oracle as ro
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 2e-5, 1e-4
+
+
+def retriever():
+    from neural_spectral_codec_b200.retrieval import WassersteinRetriever
+    return WassersteinRetriever(use_torch=True, device="cuda")
+
+
+def check_topk(idx, dist, ref_all, k):
+    """idx/dist from the GPU vs the oracle's full distance vector."""
+    order = np.argsort(ref_all, kind="stable")
+    np.testing.assert_allclose(dist, ref_all[order[:k]], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(ref_all[idx], dist, rtol=RTOL, atol=ATOL)
+    assert len(set(idx.tolist())) == len(idx)
+    gaps = np.diff(ref_all[order[:k + 1]]) if len(order) > k else np.diff(np.append(ref_all[order[:k]], np.inf))
+    clear = np.concatenate([[True], gaps[:-1] > 4 * (ATOL + RTOL * ref_all[order[1:k]])]) & \
+        (gaps > 4 * (ATOL + RTOL * ref_all[order[:k]]))
+    np.testing.assert_array_equal(idx[clear], order[:k][clear])
+
+
+def test_reference_vectors():
+    g = np.load(os.path.join(GOLDEN_DIR, "retrieval.npz"))
+    r = retriever()
+    r.add_to_database(g["database"][:100])
+    r.add_to_database(torch.from_numpy(g["database"][100:]))
+    assert r.database_size == len(g["database"])
+    np.testing.assert_array_equal(r.database_hists.cpu().numpy(), g["database"])
+    idx, top, cnt, dist = r.query_batch(g["queries"], top_k=10, return_distances=True)
+    np.testing.assert_allclose(dist.cpu().numpy(), g["distances"], rtol=RTOL, atol=ATOL)
+    assert cnt.cpu().tolist() == [10] * len(g["queries"])
+    for i in range(len(g["queries"])):
+        check_topk(idx[i].cpu().numpy(), top[i].cpu().numpy(), g["distances"][i], 10)
+        qi, qd = r.query(g["queries"][i], top_k=10)       # the reference's single-query signature
+        np.testing.assert_array_equal(qi, idx[i].cpu().numpy())
+        np.testing.assert_array_equal(qd, top[i].cpu().numpy())
+        assert qi.dtype == np.int64 and qd.dtype == np.float32
+    # the exact-copy queries retrieve themselves first at distance ~0
+    assert idx[:5, 0].cpu().tolist() == [0, 3, 9, 100, 510]
+    r.clear_database()
+    assert r.database_size == 0 and r.database_hists is None
+    e = r.query(g["queries"][0])
+    assert len(e[0]) == 0 and len(e[1]) == 0
+
+
+def test_cdf_rows_match_oracle_normalisation():
+    g = np.load(os.path.join(GOLDEN_DIR, "retrieval.npz"))
+    r = retriever()
+    r.add_to_database(g["database"])
+    db = torch.from_numpy(g["database"])
+    sums = db.sum(1, keepdim=True)
+    want = torch.cumsum(torch.where(sums > 1e-8, db / (sums + 1e-8), db), 1).numpy()
+    np.testing.assert_allclose(r.database_cdfs.cpu().numpy(), want, rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.parametrize("n_db,n_q,k", [(5000, 3, 25), (20000, 11, 100), (777, 1, 1024), (3, 2, 10)])
+def test_random_database_against_oracle(n_db, n_q, k):
+    rng = np.random.default_rng(n_db)
+    db = rng.gamma(0.5, 1.0, (n_db, 800)).astype(np.float32)
+    db /= db.sum(1, keepdims=True)
+    qs = db[rng.integers(0, n_db, n_q)] + (0.1 * rng.random((n_q, 800)) / 800).astype(np.float32)
+    r = retriever()
+    r.add_to_database(db)
+    idx, top, cnt, dist = r.query_batch(qs, top_k=k, return_distances=True)
+    kk = min(k, n_db)
+    assert idx.shape == (n_q, kk) and cnt.cpu().tolist() == [kk] * n_q
+    for i in range(n_q):
+        ref = ro.wasserstein_distance_batch(torch.from_numpy(qs[i]), torch.from_numpy(db)).numpy()
+        np.testing.assert_allclose(dist[i].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+        check_topk(idx[i].cpu().numpy(), top[i].cpu().numpy(), ref, kk)
+    again = r.query_batch(qs, top_k=k)
+    assert torch.equal(again[0], idx) and torch.equal(again[1], top)       # deterministic
+
+
+def test_ties_break_by_lower_index_and_spatial_filter():
+    rng = np.random.default_rng(1)
+    base = rng.random((40, 800)).astype(np.float32)
+    db = np.concatenate([base, base, base[:10]])          # exact duplicates -> tied distances
+    xyz = np.stack([np.arange(len(db)) * 10.0, np.zeros(len(db)), np.zeros(len(db))], 1)
+    r = retriever()
+    r.add_to_database(db, positions=xyz)
+    idx, top, cnt = r.query_batch(base[5:6], top_k=3)
+    assert idx[0].cpu().tolist() == [5, 45, 85] and float(top[0, 0]) < 1e-5
+    # spatial exclusion (two_stage_retrieval.py:158-166): rows closer than 50 m to row 45 are skipped
+    idx, top, cnt = r.query_batch(base[5:6], top_k=3, query_positions=xyz[45:46], spatial_filter_distance=50.0)
+    want_idx, want_d = ro.global_retrieval(torch.from_numpy(base[5]), xyz[45], torch.from_numpy(db), xyz, 3, 50.0)
+    assert idx[0, 0].item() == 5 and 45 not in idx[0].cpu().tolist()
+    np.testing.assert_allclose(top[0].cpu().numpy(), want_d, rtol=RTOL, atol=ATOL)
+    assert all(abs(i - 45) >= 5 for i in idx[0].cpu().tolist())
+    # fewer valid rows than top_k -> shortened answer, padded with -1 / inf
+    idx, top, cnt = r.query_batch(base[5:6], top_k=8, query_positions=xyz[45:46], spatial_filter_distance=420.0)
+    n_valid = int((np.abs(np.arange(len(db)) - 45) * 10.0 >= 420.0).sum())
+    assert cnt.item() == min(8, n_valid)
+    assert (idx[0, cnt.item():] == -1).all() and torch.isinf(top[0, cnt.item():]).all()
+
+
+def test_gathered_encoder_output_feeds_the_retriever():
+    """End of the path: descriptors from the fused encode kernel land in the database and the
+    scan retrieves itself."""
+    from neural_spectral_codec_b200 import SpectralEncoder, synth
+    small = synth.SensorShape("s", 64, -24.8, 2.0, 600)
+    pts, offs = synth.make_batch(small, 0, 64, device="cuda")
+    enc = SpectralEncoder(n_elevation=16, target_elevation_bins=16).to("cuda")
+    desc = enc.encode_points_batch(pts, offs)
+    r = retriever()
+    r.add_to_database(desc)
+    idx, top, cnt = r.query_batch(desc[:8], top_k=1)
+    assert idx[:, 0].cpu().tolist() == list(range(8))
