@@ -103,46 +103,80 @@ struct QueryArgs {
     float eps;
 };
 
+constexpr int kRowStages = 3;   // CDF rows in flight per warp (cp.async ring)
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+}
+
+// PER = elements per lane (n_bins <= 32 * PER); PER = 25 is the 800-D descriptor.
+template <int PER>
 __global__ void __launch_bounds__(kRThreads)
 wasserstein_kernel(const __grid_constant__ QueryArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int per = (a.n_bins + 31) / 32, padded = per * 32;
-    float* qcdf = smem;                                  // Q x padded, lane-contiguous layout
-    float* stage = smem + a.n_queries * padded;          // kRWarps x padded
-    // query CDFs (wasserstein.py:152-154,165), one warp per query
+    constexpr int padded = PER * 32;
+    float* qcdf = smem;                                           // Q x padded
+    float* ring = smem + a.n_queries * padded + warp * (kRowStages * padded);
+    // query CDFs (wasserstein.py:152-154,165), one warp per query, staged through the ring
     for (int q = warp; q < a.n_queries; q += kRWarps) {
-        float* row_s = stage + warp * padded;
-        for (int e = lane; e < padded; e += 32) row_s[e] = e < a.n_bins ? a.queries[(long long)q * a.n_bins + e] : 0.0f;
+        for (int e = lane; e < padded; e += 32) ring[e] = e < a.n_bins ? a.queries[(long long)q * a.n_bins + e] : 0.0f;
         __syncwarp();
         float c[kMaxPerLane];
-        row_cdf<1>(row_s, a.n_bins, per, a.eps, lane, c);
+        row_cdf<1>(ring, a.n_bins, PER, a.eps, lane, c);
 #pragma unroll
-        for (int i = 0; i < kMaxPerLane; ++i)
-            if (i < per) qcdf[q * padded + lane * per + i] = c[i];
+        for (int i = 0; i < PER; ++i) qcdf[q * padded + lane * PER + i] = c[i];
         __syncwarp();
     }
+    if (a.n_bins < padded)
+        for (int s = 0; s < kRowStages; ++s)
+            for (int e = a.n_bins + lane; e < padded; e += 32) ring[s * padded + e] = 0.0f;
     __syncthreads();
 
-    float* row_s = stage + warp * padded;
     const long long n_warps = (long long)gridDim.x * kRWarps;
-    for (long long r = (long long)blockIdx.x * kRWarps + warp; r < a.n_db; r += n_warps) {
-        const float* src = a.db_cdfs + r * a.n_bins;
-        for (int e = lane; e < padded; e += 32) row_s[e] = e < a.n_bins ? __ldcs(src + e) : 0.0f;
+    const long long r0 = (long long)blockIdx.x * kRWarps + warp;
+    const bool vec = (a.n_bins & 3) == 0;
+    auto issue = [&](long long r, int slot) {
+        if (r < a.n_db) {
+            const float* src = a.db_cdfs + r * a.n_bins;
+            float* dst = ring + slot * padded;
+            if (vec) {
+                for (int e = lane * 4; e < a.n_bins; e += 128) cp_async16(dst + e, src + e);
+            } else {
+                for (int e = lane; e < a.n_bins; e += 32) cp_async4(dst + e, src + e);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+#pragma unroll
+    for (int s = 0; s < kRowStages - 1; ++s) issue(r0 + s * n_warps, s);
+    const bool spatial = a.db_xyz != nullptr && a.query_xyz != nullptr;
+    int slot = 0;
+    for (long long r = r0; r < a.n_db; r += n_warps) {
+        issue(r + (kRowStages - 1) * n_warps, (slot + kRowStages - 1) % kRowStages);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kRowStages - 1) : "memory");
         __syncwarp();
-        float c[kMaxPerLane];
+        const float* row_s = ring + slot * padded + lane * PER;
+        float c[PER];
 #pragma unroll
-        for (int i = 0; i < kMaxPerLane; ++i) c[i] = i < per ? row_s[lane * per + i] : 0.0f;
+        for (int i = 0; i < PER; ++i) c[i] = row_s[i];
         double px = 0, py = 0, pz = 0;
-        const bool spatial = a.db_xyz != nullptr && a.query_xyz != nullptr;
-        if (spatial) { px = a.db_xyz[3 * r]; py = a.db_xyz[3 * r + 1]; pz = a.db_xyz[3 * r + 2]; }
+        if (spatial && lane == 0) { px = a.db_xyz[3 * r]; py = a.db_xyz[3 * r + 1]; pz = a.db_xyz[3 * r + 2]; }
         for (int q = 0; q < a.n_queries; ++q) {
-            const float* qc = qcdf + q * padded + lane * per;
-            float d = 0.0f;
+            const float* qc = qcdf + q * padded + lane * PER;
+            float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
-            for (int i = 0; i < kMaxPerLane; ++i)
-                if (i < per && lane * per + i < a.n_bins) d += fabsf(c[i] - qc[i]);
-            d = warp_sum(d);
+            for (int i = 0; i + 1 < PER; i += 2) {
+                d0 += fabsf(c[i] - qc[i]);
+                d1 += fabsf(c[i + 1] - qc[i + 1]);
+            }
+            if (PER & 1) d0 += fabsf(c[PER - 1] - qc[PER - 1]);
+            float d = warp_sum(d0 + d1);
             if (lane == 0) {
                 if (spatial) {   // two_stage_retrieval.py:160-164: skip keyframes closer than the threshold
                     const double dx = px - a.query_xyz[3 * q], dy = py - a.query_xyz[3 * q + 1],
@@ -153,7 +187,9 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
             }
         }
         __syncwarp();
+        slot = (slot + 1) % kRowStages;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- top-K ----------------------------------------------------------------------------------
@@ -193,37 +229,105 @@ __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* warp_t
     return r;
 }
 
+__device__ __forceinline__ void bitonic_sort_1024(unsigned long long* sel) {
+    const unsigned tid = threadIdx.x;
+    for (unsigned size = 2; size <= kTopThreads; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned j = tid ^ stride;
+            if (j > tid) {
+                const unsigned long long x = sel[tid], y = sel[j];
+                const bool up = (tid & size) == 0;
+                if ((x > y) == up) { sel[tid] = y; sel[j] = x; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// One CTA per query. Fast path: the k-th smallest of the 1024 per-thread minima bounds the k-th
+// smallest distance from above, and (unless the distances are massively tied) only a few more
+// than k keys lie under that bound: collect them, sort, done -- two passes over the keys.
+// Fallback (more than 1024 keys under the bound): 4-pass radix select of the k-th smallest
+// key with warp-aggregated histogram updates, then gather (ordered for surplus ties).
 __global__ void __launch_bounds__(kTopThreads)
 topk_kernel(const __grid_constant__ TopkArgs a) {
     __shared__ unsigned hist[256];
     __shared__ unsigned warp_tot[32];
-    __shared__ unsigned s_total, s_prefix, s_need, s_nvalid;
+    __shared__ unsigned s_total, s_prefix, s_need, s_nvalid, s_eq_total, s_fill;
     __shared__ unsigned long long sel[kTopThreads];
-    const int q = blockIdx.x, tid = threadIdx.x;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const unsigned* keys = reinterpret_cast<const unsigned*>(a.distances + (long long)q * a.n_db);
     const unsigned kInf = 0x7f800000u;
+    const long long n_round = (a.n_db + kTopThreads - 1) / kTopThreads * kTopThreads;
 
-    // number of candidates (finite distances)
-    unsigned cnt = 0;
-    for (long long i = tid; i < a.n_db; i += kTopThreads) cnt += keys[i] < kInf;
-    cnt = (unsigned)__reduce_add_sync(0xffffffffu, cnt);
-    if (tid == 0) s_nvalid = 0;
+    // pass A: per-thread minimum and the number of candidates (finite distances)
+    unsigned lmin = 0xffffffffu, valid = 0;
+    {
+        long long i = tid;
+        for (; i + 3 * kTopThreads < a.n_db; i += 4 * kTopThreads) {
+            const unsigned k0 = keys[i], k1 = keys[i + kTopThreads], k2 = keys[i + 2 * kTopThreads],
+                           k3 = keys[i + 3 * kTopThreads];
+            lmin = min(min(lmin, k0), min(k1, min(k2, k3)));
+            valid += (k0 < kInf) + (k1 < kInf) + (k2 < kInf) + (k3 < kInf);
+        }
+        for (; i < a.n_db; i += kTopThreads) {
+            const unsigned k0 = keys[i];
+            lmin = min(lmin, k0);
+            valid += k0 < kInf;
+        }
+    }
+    if (tid == 0) { s_nvalid = 0; s_fill = 0; }
+    sel[tid] = (unsigned long long)lmin << 32;
     __syncthreads();
-    if ((tid & 31) == 0) atomicAdd(&s_nvalid, cnt);
-    __syncthreads();
+    valid = (unsigned)__reduce_add_sync(0xffffffffu, valid);
+    if (lane == 0) atomicAdd(&s_nvalid, valid);
+    bitonic_sort_1024(sel);                       // ends with a barrier
     const unsigned k = min((unsigned)a.k, s_nvalid);
-
-    // radix select: after the loop `prefix` is the k-th smallest key and `need` how many keys
-    // equal to it are taken (those with the lowest indices).
-    unsigned prefix = 0, need = k;
+    const unsigned bound = k > 0 ? min((unsigned)(sel[k - 1] >> 32), kInf - 1u) : 0u;
+    __syncthreads();
+    sel[tid] = ~0ull;
+    __syncthreads();
+    // pass B: collect every key <= bound
     if (k > 0) {
+        long long i = tid;
+        for (; i + 3 * kTopThreads < a.n_db; i += 4 * kTopThreads) {
+            unsigned kk[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) kk[u] = keys[i + u * kTopThreads];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (kk[u] <= bound) {
+                    const unsigned pos = atomicAdd(&s_fill, 1u);
+                    if (pos < kTopThreads) sel[pos] = ((unsigned long long)kk[u] << 32) | (unsigned)(i + u * kTopThreads);
+                }
+        }
+        for (; i < a.n_db; i += kTopThreads) {
+            const unsigned k0 = keys[i];
+            if (k0 <= bound) {
+                const unsigned pos = atomicAdd(&s_fill, 1u);
+                if (pos < kTopThreads) sel[pos] = ((unsigned long long)k0 << 32) | (unsigned)i;
+            }
+        }
+    }
+    __syncthreads();
+    const bool overflow = s_fill > kTopThreads;
+    __syncthreads();
+
+    if (overflow) {
+        unsigned prefix = 0, need = k;
         for (int shift = 24; shift >= 0; shift -= 8) {
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
             const unsigned mask_hi = shift == 24 ? 0u : (0xffffffffu << (shift + 8));
-            for (long long i = tid; i < a.n_db; i += kTopThreads) {
-                const unsigned key = keys[i];
-                if ((key & mask_hi) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            for (long long i = tid; i < n_round; i += kTopThreads) {
+                const unsigned key = i < a.n_db ? keys[i] : 0xffffffffu;
+                const bool act = i < a.n_db && (key & mask_hi) == prefix;
+                const unsigned amask = __ballot_sync(0xffffffffu, act);
+                if (act) {
+                    const unsigned bin = (key >> shift) & 255u;
+                    const unsigned peers = __match_any_sync(amask, bin);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[bin], (unsigned)__popc(peers));
+                }
             }
             __syncthreads();
             if (tid == 0) {
@@ -234,48 +338,38 @@ topk_kernel(const __grid_constant__ TopkArgs a) {
                 }
                 s_prefix = prefix | (b << shift);
                 s_need = need - acc;
+                s_eq_total = hist[b];      // after the last pass: keys equal to the k-th smallest
             }
             __syncthreads();
             prefix = s_prefix;
             need = s_need;
         }
-    }
-    // ordered gather: all keys < prefix, and the first `need` keys == prefix in index order
-    unsigned base_less = 0, base_eq = 0;
-    const unsigned n_less = k - need;
-    sel[tid] = ~0ull;
-    __syncthreads();
-    if (k > 0) {
-        for (long long i0 = 0; i0 < a.n_db; i0 += kTopThreads) {
-            const long long i = i0 + tid;
-            const unsigned key = i < a.n_db ? keys[i] : 0xffffffffu;
-            const unsigned less = key < prefix, eq = key == prefix;
-            unsigned tot_less, tot_eq;
-            const unsigned pl = block_excl_scan(less, warp_tot, &s_total);
-            tot_less = s_total;
-            __syncthreads();
-            const unsigned pe = block_excl_scan(eq, warp_tot, &s_total);
-            tot_eq = s_total;
-            __syncthreads();
-            if (less) sel[base_less + pl] = ((unsigned long long)key << 32) | (unsigned)i;
-            if (eq && base_eq + pe < need) sel[n_less + base_eq + pe] = ((unsigned long long)key << 32) | (unsigned)i;
-            base_less += tot_less;
-            base_eq += tot_eq;
+        // every key < prefix and `need` keys == prefix; with surplus ties the lowest indices win
+        const unsigned n_less = k - need;
+        sel[tid] = ~0ull;
+        if (tid == 0) s_fill = 0;
+        __syncthreads();
+        const bool all_eq = s_eq_total == need;
+        for (long long i = tid; i < a.n_db; i += kTopThreads) {
+            const unsigned key = keys[i];
+            if (key < prefix || (all_eq && key == prefix))
+                sel[atomicAdd(&s_fill, 1u)] = ((unsigned long long)key << 32) | (unsigned)i;
         }
-    }
-    __syncthreads();
-    // bitonic sort of kTopThreads packed (distance bits, index) keys, ascending; unused = ~0
-    for (unsigned size = 2; size <= kTopThreads; size <<= 1) {
-        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
-            const unsigned j = tid ^ stride;
-            if (j > (unsigned)tid) {
-                const unsigned long long x = sel[tid], y = sel[j];
-                const bool up = (tid & size) == 0;
-                if ((x > y) == up) { sel[tid] = y; sel[j] = x; }
+        if (!all_eq) {
+            unsigned base_eq = 0;
+            for (long long i0 = 0; i0 < a.n_db && base_eq < need; i0 += kTopThreads) {
+                const long long i = i0 + tid;
+                const unsigned eq = i < a.n_db && keys[i] == prefix;
+                const unsigned pe = block_excl_scan(eq, warp_tot, &s_total);
+                if (eq && base_eq + pe < need)
+                    sel[n_less + base_eq + pe] = ((unsigned long long)prefix << 32) | (unsigned)i;
+                base_eq += s_total;
+                __syncthreads();
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
+    bitonic_sort_1024(sel);   // packed (distance bits, index) ascending; unused slots = ~0
     if (tid < a.k) {
         const bool ok = (unsigned)tid < k;
         a.top_idx[(long long)q * a.k + tid] = ok ? (long long)(unsigned)(sel[tid] & 0xffffffffull) : -1;
@@ -335,7 +429,6 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
     int sms = 0;
     int st = sm_count(&sms);
     if (st != NSC_OK) return st;
-    const int padded = ((n_bins + 31) / 32) * 32;
     if (n_db > 0) {
         for (int q0 = 0; q0 < n_queries; q0 += kMaxQueries) {
             QueryArgs a;
@@ -349,13 +442,22 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             a.n_db = n_db;
             a.n_bins = n_bins;
             a.eps = epsilon;
-            const size_t smem = (size_t)(a.n_queries + kRWarps) * padded * 4;
-            cudaError_t e = cudaFuncSetAttribute(wasserstein_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            void (*kern)(const QueryArgs) = nullptr;
+            int per = (n_bins + 31) / 32;
+            if (per <= 8) { kern = wasserstein_kernel<8>; per = 8; }
+            else if (per <= 16) { kern = wasserstein_kernel<16>; per = 16; }
+            else if (per <= 25) { kern = wasserstein_kernel<25>; per = 25; }
+            else { kern = wasserstein_kernel<32>; per = 32; }
+            const size_t smem = (size_t)(a.n_queries + kRWarps * kRowStages) * per * 32 * 4;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return record_cuda(e);
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRThreads, smem);
+            if (e != cudaSuccess) return record_cuda(e);
+            if (per_sm < 1) return NSC_ERR_BAD_PARAMS;
             long long grid = (n_db + kRWarps - 1) / kRWarps;
-            if (grid > (long long)sms * 4) grid = (long long)sms * 4;
-            wasserstein_kernel<<<(int)grid, kRThreads, smem, s>>>(a);
+            if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
+            kern<<<(int)grid, kRThreads, smem, s>>>(a);
             e = cudaGetLastError();
             if (e != cudaSuccess) return record_cuda(e);
         }

@@ -111,6 +111,28 @@ def test_ties_break_by_lower_index_and_spatial_filter():
     assert (idx[0, cnt.item():] == -1).all() and torch.isinf(top[0, cnt.item():]).all()
 
 
+def test_massive_ties_take_the_radix_path():
+    """More than 1024 database rows at exactly the k-th distance overflow the candidate buffer
+    of the fast path; the radix-select fallback must still return the lowest indices."""
+    rng = np.random.default_rng(2)
+    row = rng.random(800).astype(np.float32)
+    near = (row + 0.5 * rng.random((7, 800)).astype(np.float32) / 800)
+    db = np.concatenate([np.tile(row, (3000, 1)), near, np.tile(row, (50, 1))]).astype(np.float32)
+    q = row * np.float32(1.5)                      # unnormalised query: same shape, distance ~0 to `row`
+    r = retriever()
+    r.add_to_database(db)
+    idx, top, cnt = r.query_batch(q, top_k=20)
+    assert idx[0].cpu().tolist() == list(range(20))
+    assert float(top[0].max()) == float(top[0].min())
+    idx, top, cnt = r.query_batch(near[3], top_k=3)
+    ref = ro.wasserstein_distance_batch(torch.from_numpy(near[3]), torch.from_numpy(db)).numpy()
+    assert idx[0, 0].item() == 3003
+    np.testing.assert_allclose(top[0].cpu().numpy(), np.sort(ref)[:3], rtol=RTOL, atol=ATOL)
+    # 5 perturbed rows are nearer than the 3050 tied copies of `row`: ties go to the lowest indices
+    idx, top, cnt = r.query_batch(near[3], top_k=12)
+    assert idx[0].cpu().tolist() == [3003, 3006, 3000, 3002, 3005, 0, 1, 2, 3, 4, 5, 6]
+
+
 def test_gathered_encoder_output_feeds_the_retriever():
     """End of the path: descriptors from the fused encode kernel land in the database and the
     scan retrieves itself."""
