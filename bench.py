@@ -36,8 +36,13 @@ N_SCANS = 4541            # KITTI sequence 00 length (BASELINE.json configs[1])
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 
 
-def workload_name(n):
-    return f"synthetic KITTI seq-00-length batch: {n} HDL-64-shaped scans x ~120k xyzi points per GPU"
+SHAPE_DESC = {"hdl64": "HDL-64-shaped scans x ~120k xyzi points", "hdl32": "NCLT HDL-32-shaped scans x ~70k xyzi points",
+              "beam128": "128-beam dense scans x ~260k xyzi points"}
+
+
+def workload_name(n, shape="hdl64", shuffle=False):
+    head = "synthetic KITTI seq-00-length batch" if shape == "hdl64" else "synthetic batch"
+    return f"{head}: {n} {SHAPE_DESC[shape]} per GPU" + (" (shuffled point order)" if shuffle else "")
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -173,7 +178,8 @@ def run_gpu_arm(args):
 
     # synthetic scans of this rank, generated on the device from per-scan seeds
     first = rank * n_scans
-    scans = [synth.make_scan(synth.HDL64, first + i, device=dev) for i in range(n_scans)]
+    scans = [synth.make_scan(synth.SHAPES[args.shape], first + i, device=dev, shuffle=args.shuffle)
+             for i in range(n_scans)]
     counts = torch.tensor([0] + [s.shape[0] for s in scans], dtype=torch.int64)
     offsets = torch.cumsum(counts, 0).to(dev)
     points = torch.cat(scans, 0)
@@ -242,7 +248,7 @@ def run_gpu_arm(args):
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if tj.get("scans") == n_scans:
+        if tj.get("scans") == n_scans and args.shape == "hdl64" and not args.shuffle:
             traffic = tj.get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "kernel": "encode_points_kernel<4,0>",
@@ -286,9 +292,9 @@ def run_gpu_arm(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n_scans), "scans_per_gpu": n_scans,
+            "config": {"workload": workload_name(n_scans, args.shape, args.shuffle), "scans_per_gpu": n_scans,
                        "points_per_gpu": total_points, "input_bytes_per_gpu": 16 * total_points,
-                       "l2": "inputs (8.7 GB) larger than L2, no flush needed",
+                       "l2": f"inputs ({16 * total_points / 1e9:.1f} GB) larger than L2, no flush needed",
                        "gather": ("none (single GPU)" if world == 1 else args.gather),
                        "encoder": "n_elevation=16 n_azimuth=360 n_bins=50 alpha=2.0 target_rows=16"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
@@ -323,6 +329,9 @@ def main():
     ap.add_argument("--e2e-scans", type=int, default=1024, help="scans per end-to-end step")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shape", default="hdl64", choices=sorted(SHAPE_DESC),
+                    help="sensor shape of the synthetic scans (BASELINE.json configs 2-4; default = the metric's config)")
+    ap.add_argument("--shuffle", action="store_true", help="random point order inside each scan")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
