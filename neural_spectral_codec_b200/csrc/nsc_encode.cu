@@ -7,6 +7,8 @@
 
 #include <mutex>
 
+#include <cooperative_groups.h>
+
 #include "nsc_point.h"
 #include "nsc_tail.cuh"
 
@@ -90,6 +92,138 @@ __device__ __forceinline__ void project_point(float x, float y, float z, const D
     scatter_min(img_biased, row_b, col_b, key);
 }
 
+// Point pass over points [beg, beg + n) of the concatenated buffer: every kept point lowers the
+// key of its pixel in the shared-memory min image. CTA-collective (no barrier inside).
+template <int STRIDE, int ROWMODE, int FEED>
+__device__ __forceinline__ void point_pass(const float* __restrict__ points, long long beg, int n,
+                                           const DeviceParams& dp, uint32_t img_biased,
+                                           unsigned char* ring) {
+    const int tid = threadIdx.x;
+    if (FEED == kFeedCpAsync) {
+        // Each thread streams its own points through a private kCpDepth-deep shared-memory
+        // ring of 16-byte cp.async copies. No cross-thread barrier is needed: a thread only
+        // reads what it copied itself. Stage `it` holds points it*kStagePoints +
+        // u*kThreads + tid, u < kCpPts; stage it + kCpDepth - 1 is issued before stage it
+        // is consumed.
+        constexpr int kStagePoints = kCpPts * kThreads;
+        constexpr int kSlotBytes = kCpPts * kThreads * 16;
+        const float4* gp = reinterpret_cast<const float4*>(points) + beg + tid;
+        const uint32_t ring_t = smem_u32(ring) + tid * 16;
+        const int n_full = n / kStagePoints;              // stages with every point in range
+        const int n_iter = (n + kStagePoints - 1) / kStagePoints;
+        auto issue_checked = [&](int it) {
+            if (it < n_iter) {
+#pragma unroll
+                for (int u = 0; u < kCpPts; ++u) {
+                    const int i = it * kStagePoints + u * kThreads;
+                    if (i + tid < n)
+                        cp_async16(ring_t + (it % kCpDepth) * kSlotBytes + u * (kThreads * 16), gp + i);
+                }
+            }
+            cp_async_commit();
+        };
+#pragma unroll
+        for (int d = 0; d < kCpDepth - 1; ++d) issue_checked(d);
+        int it = 0;
+        // Main trips: kCpDepth stages per trip so every ring slot is a compile-time offset and
+        // no bounds checks remain (all stages touched are full).
+        for (; it + 2 * kCpDepth - 2 < n_full; it += kCpDepth) {
+            const float4* g = gp + (long long)it * kStagePoints;
+#pragma unroll
+            for (int s = 0; s < kCpDepth; ++s) {
+#pragma unroll
+                for (int u = 0; u < kCpPts; ++u)
+                    cp_async16(ring_t + ((s + kCpDepth - 1) % kCpDepth) * kSlotBytes + u * (kThreads * 16),
+                               g + (s + kCpDepth - 1) * kStagePoints + u * kThreads);
+                cp_async_commit();
+                cp_async_wait<kCpDepth - 1>();
+                float4 v[kCpPts];
+#pragma unroll
+                for (int u = 0; u < kCpPts; ++u) v[u] = lds128(ring_t + s * kSlotBytes + u * (kThreads * 16));
+#pragma unroll
+                for (int u = 0; u < kCpPts; ++u)
+                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+            }
+        }
+        // Remaining stages (the last few full ones and the partial one), bounds-checked.
+        for (; it < n_iter; ++it) {
+            issue_checked(it + kCpDepth - 1);
+            cp_async_wait<kCpDepth - 1>();
+#pragma unroll
+            for (int u = 0; u < kCpPts; ++u) {
+                const int i = it * kStagePoints + u * kThreads + tid;
+                const float4 v = lds128(ring_t + (it % kCpDepth) * kSlotBytes + u * (kThreads * 16));
+                project_point<ROWMODE>(v.x, v.y, v.z, dp, img_biased, i < n);
+            }
+        }
+        cp_async_wait<0>();
+    } else if (STRIDE == 4) {
+        const float4* p4 = reinterpret_cast<const float4*>(points) + beg;
+        for (int base = 0; base < n; base += kThreads * kUnroll) {
+            float4 v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = base + u * kThreads + tid;
+                v[u] = i < n ? __ldcs(p4 + i) : make_float4(NAN, NAN, NAN, 0.0f);
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+        }
+    } else {
+        const float* p = points + beg * 3;
+        for (int base = 0; base < n; base += kThreads * kUnroll) {
+            float x[kUnroll], y[kUnroll], z[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int i = base + u * kThreads + tid;
+                const bool in = i < n;
+                x[u] = in ? __ldcs(p + 3 * (long long)i) : NAN;
+                y[u] = in ? __ldcs(p + 3 * (long long)i + 1) : NAN;
+                z[u] = in ? __ldcs(p + 3 * (long long)i + 2) : NAN;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u)
+                project_point<ROWMODE>(x[u], y[u], z[u], dp, img_biased);
+        }
+    }
+}
+
+// Everything after the scatter for one scan: keys -> ranges, interpolation, (optional) image
+// output, spectrum, bins, normalisation, descriptor store. CTA-collective.
+__device__ __forceinline__ void finish_scan(const EncodeArgs& a, const DeviceParams& dp,
+                                            const TailSmem& S, int scan) {
+    const int tid = threadIdx.x;
+    const int D = dp.T * dp.n_bins;
+    const uint32_t* img = reinterpret_cast<const uint32_t*>(S.img);
+    // bits of min s -> range = sqrt_rn(s); empty -> 0 (range_image.py:162,:214). Column 360
+    // (azimuth exactly 2 pi) belongs to column 0.
+    for (int i = tid; i < dp.E * kAz; i += kThreads) {
+        const int r = i / kAz, c = i - r * kAz;
+        uint32_t b = img[r * kPitch + c];
+        if (c == 0) b = min(b, img[r * kPitch + kAz]);
+        const float v = (b == kInfBits) ? 0.0f : __fsqrt_rn(__uint_as_float(b));
+        S.img[r * kPitch + c] = v;
+        if (a.img_out && a.stage == NSC_STAGE_PROJECTED)
+            a.img_out[(long long)scan * dp.E * kAz + i] = v;
+    }
+    __syncthreads();
+    build_masks(S, dp.E);
+    __syncthreads();
+    interpolate_and_fill(S, dp.E, dp.interpolate != 0);
+    if (a.img_out && a.stage == NSC_STAGE_INTERPOLATED) {
+        for (int i = tid; i < dp.E * kAz; i += kThreads) {
+            const int r = i / kAz, c = i - r * kAz;
+            a.img_out[(long long)scan * dp.E * kAz + i] = S.img[S.src[r] * kPitch + c];
+        }
+    }
+    if (a.out || a.peers.n > 0) {
+        spectrum_and_bins(S, dp, dp.E);
+        normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
+                            a.peers.row0 + scan);
+    }
+}
+
 template <int STRIDE, int ROWMODE, int FEED>
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
 encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
@@ -101,7 +235,6 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
     const uint32_t img_biased = smem_u32(img) - kFloorBias * (uint32_t)(kPitch * 4 + 4);
     const int tid = threadIdx.x;
     const int n_pix = dp.E * kPitch;
-    const int D = dp.T * dp.n_bins;
 
     init_twiddles(S.tw);
 
@@ -112,126 +245,54 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
         __syncthreads();
         const int scan = s_scan;
         if (scan >= a.n_scans) break;
-
         const long long beg = a.offsets[scan] - a.origin;
         const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
+        point_pass<STRIDE, ROWMODE, FEED>(a.points, beg, n, dp, img_biased, smem_raw + L.ring_off);
+        __syncthreads();
+        finish_scan(a, dp, S, scan);
+    }
+}
 
-        if (FEED == kFeedCpAsync) {
-            // Each thread streams its own points through a private kCpDepth-deep shared-memory
-            // ring of 16-byte cp.async copies. No cross-thread barrier is needed: a thread only
-            // reads what it copied itself. Stage `it` holds points it*kStagePoints +
-            // u*kThreads + tid, u < kCpPts; stage it + kCpDepth - 1 is issued before stage it
-            // is consumed.
-            constexpr int kStagePoints = kCpPts * kThreads;
-            constexpr int kSlotBytes = kCpPts * kThreads * 16;
-            const float4* gp = reinterpret_cast<const float4*>(a.points) + beg + tid;
-            const uint32_t ring_t = smem_u32(smem_raw + L.ring_off) + tid * 16;
-            const int n_full = n / kStagePoints;              // stages with every point in range
-            const int n_iter = (n + kStagePoints - 1) / kStagePoints;
-            auto issue_checked = [&](int it) {
-                if (it < n_iter) {
-#pragma unroll
-                    for (int u = 0; u < kCpPts; ++u) {
-                        const int i = it * kStagePoints + u * kThreads;
-                        if (i + tid < n)
-                            cp_async16(ring_t + (it % kCpDepth) * kSlotBytes + u * (kThreads * 16), gp + i);
-                    }
-                }
-                cp_async_commit();
-            };
-#pragma unroll
-            for (int d = 0; d < kCpDepth - 1; ++d) issue_checked(d);
-            int it = 0;
-            // Main trips: kCpDepth stages per trip so every ring slot is a compile-time offset and
-            // no bounds checks remain (all stages touched are full).
-            for (; it + 2 * kCpDepth - 2 < n_full; it += kCpDepth) {
-                const float4* g = gp + (long long)it * kStagePoints;
-#pragma unroll
-                for (int s = 0; s < kCpDepth; ++s) {
-#pragma unroll
-                    for (int u = 0; u < kCpPts; ++u)
-                        cp_async16(ring_t + ((s + kCpDepth - 1) % kCpDepth) * kSlotBytes + u * (kThreads * 16),
-                                   g + (s + kCpDepth - 1) * kStagePoints + u * kThreads);
-                    cp_async_commit();
-                    cp_async_wait<kCpDepth - 1>();
-                    float4 v[kCpPts];
-#pragma unroll
-                    for (int u = 0; u < kCpPts; ++u) v[u] = lds128(ring_t + s * kSlotBytes + u * (kThreads * 16));
-#pragma unroll
-                    for (int u = 0; u < kCpPts; ++u)
-                        project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
-                }
-            }
-            // Remaining stages (the last few full ones and the partial one), bounds-checked.
-            for (; it < n_iter; ++it) {
-                issue_checked(it + kCpDepth - 1);
-                cp_async_wait<kCpDepth - 1>();
-#pragma unroll
-                for (int u = 0; u < kCpPts; ++u) {
-                    const int i = it * kStagePoints + u * kThreads + tid;
-                    const float4 v = lds128(ring_t + (it % kCpDepth) * kSlotBytes + u * (kThreads * 16));
-                    project_point<ROWMODE>(v.x, v.y, v.z, dp, img_biased, i < n);
-                }
-            }
-            cp_async_wait<0>();
-        } else if (STRIDE == 4) {
-            const float4* p4 = reinterpret_cast<const float4*>(a.points) + beg;
-            for (int base = 0; base < n; base += kThreads * kUnroll) {
-                float4 v[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int i = base + u * kThreads + tid;
-                    v[u] = i < n ? __ldcs(p4 + i) : make_float4(NAN, NAN, NAN, 0.0f);
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
-            }
-        } else {
-            const float* p = a.points + beg * 3;
-            for (int base = 0; base < n; base += kThreads * kUnroll) {
-                float x[kUnroll], y[kUnroll], z[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int i = base + u * kThreads + tid;
-                    const bool in = i < n;
-                    x[u] = in ? __ldcs(p + 3 * (long long)i) : NAN;
-                    y[u] = in ? __ldcs(p + 3 * (long long)i + 1) : NAN;
-                    z[u] = in ? __ldcs(p + 3 * (long long)i + 2) : NAN;
-                }
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-                    project_point<ROWMODE>(x[u], y[u], z[u], dp, img_biased);
-            }
-        }
-        __syncthreads();
+// Small batches (fewer scans than SMs / cluster size): one thread-block CLUSTER per scan. The
+// CTAs of a cluster each scatter a contiguous slice of the scan into their own shared-memory
+// image; after a cluster barrier the leader min-reduces the other images through distributed
+// shared memory and runs the tail. Cuts the latency of a single 120 k-point scan from one SM's
+// worth of time to roughly 1/cluster_size of it plus the tail.
+template <int STRIDE, int ROWMODE, int FEED>
+__global__ void __launch_bounds__(kThreads, 1)
+encode_points_split_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank(), csize = cluster.num_blocks();
+    const SmemLayout L(dp.E, dp.T, dp.n_bins, ring_bytes_of(FEED));
+    const TailSmem S(smem_raw, L);
+    uint32_t* img = reinterpret_cast<uint32_t*>(S.img);
+    const uint32_t img_biased = smem_u32(img) - kFloorBias * (uint32_t)(kPitch * 4 + 4);
+    const int tid = threadIdx.x;
+    const int n_pix = dp.E * kPitch;
+    const int scan = blockIdx.x / csize;      // grid = n_scans * cluster size
 
-        // bits of min s -> range = sqrt_rn(s); empty -> 0 (range_image.py:162,:214). Column 360
-        // (azimuth exactly 2 pi) belongs to column 0.
-        for (int i = tid; i < dp.E * kAz; i += kThreads) {
-            const int r = i / kAz, c = i - r * kAz;
-            uint32_t b = img[r * kPitch + c];
-            if (c == 0) b = min(b, img[r * kPitch + kAz]);
-            const float v = (b == kInfBits) ? 0.0f : __fsqrt_rn(__uint_as_float(b));
-            S.img[r * kPitch + c] = v;
-            if (a.img_out && a.stage == NSC_STAGE_PROJECTED)
-                a.img_out[(long long)scan * dp.E * kAz + i] = v;
+    if (rank == 0) init_twiddles(S.tw);
+    for (int i = tid; i < n_pix; i += kThreads) img[i] = kInfBits;
+    __syncthreads();
+    const long long beg = a.offsets[scan] - a.origin;
+    const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
+    const int per = (n + (int)csize - 1) / (int)csize;
+    const int lo = min(n, (int)rank * per), hi = min(n, lo + per);
+    point_pass<STRIDE, ROWMODE, FEED>(a.points, beg + lo, hi - lo, dp, img_biased, smem_raw + L.ring_off);
+    cluster.sync();                           // every partial image is complete
+    if (rank == 0) {
+        for (int i = tid; i < n_pix; i += kThreads) {
+            uint32_t m = img[i];
+            for (unsigned r = 1; r < csize; ++r) m = min(m, cluster.map_shared_rank(img, r)[i]);
+            img[i] = m;
         }
+    }
+    cluster.sync();                           // peers may exit only after the leader has read them
+    if (rank == 0) {
         __syncthreads();
-        build_masks(S, dp.E);
-        __syncthreads();
-        interpolate_and_fill(S, dp.E, dp.interpolate != 0);
-        if (a.img_out && a.stage == NSC_STAGE_INTERPOLATED) {
-            for (int i = tid; i < dp.E * kAz; i += kThreads) {
-                const int r = i / kAz, c = i - r * kAz;
-                a.img_out[(long long)scan * dp.E * kAz + i] = S.img[S.src[r] * kPitch + c];
-            }
-        }
-        if (a.out || a.peers.n > 0) {
-            spectrum_and_bins(S, dp, dp.E);
-            normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
-                                a.peers.row0 + scan);
-        }
+        finish_scan(a, dp, S, scan);
     }
 }
 
@@ -359,16 +420,55 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     int feed = feed_override >= 0 ? feed_override : kDefaultFeed;
     if (stride != 4) feed = kFeedLdg;
     const SmemLayout L(dp.E, dp.T, dp.n_bins, ring_bytes_of(feed));
+    // Few scans: one cluster of 2/4/8 CTAs per scan (NSC_SPLIT=0 disables, for A/B runs).
+    static const bool split_allowed = [] {
+        const char* e = getenv("NSC_SPLIT");
+        return !(e && e[0] == '0');
+    }();
+    int csize = 1;
+    if (split_allowed) {
+        if (n_scans * 8 <= di.sms) csize = 8;
+        else if (n_scans * 4 <= di.sms) csize = 4;
+        else if (n_scans * 2 <= di.sms) csize = 2;
+    }
     void (*kernel)(const EncodeArgs, const DeviceParams) = nullptr;
+    const bool poly = dp.row_mode == kRowPoly;
+    if (csize > 1) {
+        if (feed == kFeedCpAsync)
+            kernel = poly ? encode_points_split_kernel<4, kRowPoly, kFeedCpAsync>
+                          : encode_points_split_kernel<4, kRowSearch, kFeedCpAsync>;
+        else if (stride == 4)
+            kernel = poly ? encode_points_split_kernel<4, kRowPoly, kFeedLdg>
+                          : encode_points_split_kernel<4, kRowSearch, kFeedLdg>;
+        else
+            kernel = poly ? encode_points_split_kernel<3, kRowPoly, kFeedLdg>
+                          : encode_points_split_kernel<3, kRowSearch, kFeedLdg>;
+        if (L.total > di.max_smem_optin) return NSC_ERR_BAD_PARAMS;
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+        if (e != cudaSuccess) return record_cuda(e);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_scans * csize));
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = (size_t)L.total;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return record_cuda(cudaLaunchKernelEx(&cfg, kernel, a, dp));
+    }
     if (feed == kFeedCpAsync) {
-        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedCpAsync>
-                                         : encode_points_kernel<4, kRowSearch, kFeedCpAsync>;
+        kernel = poly ? encode_points_kernel<4, kRowPoly, kFeedCpAsync>
+                      : encode_points_kernel<4, kRowSearch, kFeedCpAsync>;
     } else if (stride == 4) {
-        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<4, kRowPoly, kFeedLdg>
-                                         : encode_points_kernel<4, kRowSearch, kFeedLdg>;
+        kernel = poly ? encode_points_kernel<4, kRowPoly, kFeedLdg>
+                      : encode_points_kernel<4, kRowSearch, kFeedLdg>;
     } else {
-        kernel = dp.row_mode == kRowPoly ? encode_points_kernel<3, kRowPoly, kFeedLdg>
-                                         : encode_points_kernel<3, kRowSearch, kFeedLdg>;
+        kernel = poly ? encode_points_kernel<3, kRowPoly, kFeedLdg>
+                      : encode_points_kernel<3, kRowSearch, kFeedLdg>;
     }
     int per_sm = 0;
     st = configure(kernel, L.total, di, &per_sm);

@@ -150,6 +150,28 @@ def test_batch_equals_single_and_is_deterministic():
     np.testing.assert_array_equal(enc.encode_points(pts[:o[1]][perm].numpy()).cpu().numpy(), a[0])
 
 
+def test_cluster_split_equals_persistent_kernel():
+    """Small batches run one thread-block cluster per scan (2/4/8 CTAs share a scan through
+    distributed shared memory); large ones run one persistent CTA per scan. Same bits."""
+    from neural_spectral_codec_b200 import synth
+    small = synth.SensorShape("s", 64, -24.8, 2.0, 500)
+    pts, offs = synth.make_batch(small, 40, 200)           # 200 scans -> persistent kernel
+    pts, offs = pts.cuda(), offs.cuda()
+    enc = make_encoder()
+    full = enc.encode_points_batch(pts, offs).cpu().numpy()
+    o = offs.cpu().numpy()
+    cfg = orc.OracleConfig()
+    for first, count in ((0, 1), (7, 3), (20, 18), (50, 30), (100, 60)):   # cluster sizes 8, 8, 8, 4, 2
+        sub = enc.encode_points_batch(pts[o[first]:o[first + count]], offs[first:first + count + 1] - offs[first])
+        np.testing.assert_array_equal(sub.cpu().numpy(), full[first:first + count])
+    ref = orc.encode_points(pts[o[199]:o[200]].cpu().numpy(), cfg).numpy()
+    assert np.abs(full[199] - ref).max() < 1e-4
+    # 12-byte points through the cluster path, odd slice starts
+    xyz = pts[:, :3].contiguous()
+    sub3 = enc.encode_points_batch(xyz[o[7]:o[10]], offs[7:11] - offs[7]).cpu().numpy()
+    np.testing.assert_array_equal(sub3, full[7:10])
+
+
 def test_ragged_batch_with_empty_and_filtered_scans():
     enc = make_encoder()
     cfg = orc.OracleConfig()
