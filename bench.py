@@ -176,6 +176,16 @@ def run_gpu_arm(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # keep each rank (and the pinned host buffers it allocates) on the CPUs next to its GPU
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[local_rank]) if visible else local_rank
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        except Exception:
+            pass
+    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -288,7 +298,7 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        per_core = 8
+        per_core = 24
         v, n = cpu_oracle_throughput(per_core, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n} HDL-64 scans ({per_core} per core), oracle/nsc_oracle.py, "

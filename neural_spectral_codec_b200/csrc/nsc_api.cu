@@ -267,7 +267,8 @@ int nsc_test_host_classify(const float* h_points, int point_stride, int64_t n_po
     for (int64_t i = 0; i < n_points; ++i) {
         const float* q = h_points + i * point_stride;
         uint32_t row_b = 0, col_b = 0;
-        const bool keep = classify(q[0], q[1], q[2], dp, dp.row_mode, row_b, col_b) != 0xffffffffu;
+        const uint32_t key = classify(q[0], q[1], q[2], dp, dp.row_mode, row_b, col_b);
+        const bool keep = key != 0xffffffffu && !key_is_empty(key, dp);
         h_keep[i] = keep ? 1 : 0;
         h_row[i] = keep ? (int32_t)(row_b - kFloorBias) : -1;
         int32_t c = keep ? (int32_t)(col_b - kFloorBias) : -1;

@@ -16,6 +16,9 @@ namespace nsc {
 
 namespace {
 
+#ifndef NSC_PRECHECK
+#define NSC_PRECHECK 1
+#endif
 constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread (LDG feed)
 
 struct EncodeArgs {
@@ -72,6 +75,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void scatter_min(uint32_t img_biased, uint32_t row_b, uint32_t col_b,
                                             uint32_t key) {
     const uint32_t addr = row_b * (uint32_t)(kPitch * 4) + (col_b * 4u + img_biased);
+#if NSC_PRECHECK
     uint32_t cur;
     asm("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(addr));
     asm volatile(
@@ -81,6 +85,9 @@ __device__ __forceinline__ void scatter_min(uint32_t img_biased, uint32_t row_b,
         "@p red.shared.min.u32 [%0], %1;\n"
         "}\n" ::"r"(addr), "r"(key), "r"(cur)
         : "memory");
+#else
+    asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(addr), "r"(key) : "memory");
+#endif
 }
 
 template <int ROWMODE>
@@ -202,7 +209,7 @@ __device__ __forceinline__ void finish_scan(const EncodeArgs& a, const DevicePar
         const int r = i / kAz, c = i - r * kAz;
         uint32_t b = img[r * kPitch + c];
         if (c == 0) b = min(b, img[r * kPitch + kAz]);
-        const float v = (b == kInfBits) ? 0.0f : __fsqrt_rn(__uint_as_float(b));
+        const float v = key_is_empty(b, dp) ? 0.0f : __fsqrt_rn(__uint_as_float(b));
         S.img[r * kPitch + c] = v;
         if (a.img_out && a.stage == NSC_STAGE_PROJECTED)
             a.img_out[(long long)scan * dp.E * kAz + i] = v;
