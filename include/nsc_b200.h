@@ -192,6 +192,19 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
                           float* d_distances, int top_k, int64_t* d_top_idx, float* d_top_dist,
                           int32_t* d_top_count, void* stream);
 
+/* ---- descriptor wire format (fourth "next" row) --------------------------- */
+/* Replaces HistogramQuantizer.quantize / dequantize (reference src/encoding/quantization.py
+ * :131-167, :169-192) for n_rows rows at once and any row length <= 4096 (the reference class is
+ * instantiated for 50 bins; the 800-D descriptor quantises to 1600 bytes). Integers are
+ * bit-identical to the reference's: the row sum follows NumPy's pairwise float32 order.
+ *   quantize:   h / (sum h + eps) where sum h > eps, round-half-even(h * 65535), rounding error
+ *               added to the first largest bin so that the row sums to 65535
+ *   dequantize: q / (sum q + eps), or 1 / n_bins where sum q <= eps */
+int nsc_quantize_histograms(const float* d_hist, int64_t n_rows, int n_bins, float epsilon,
+                            uint16_t* d_quantized, void* stream);
+int nsc_dequantize_histograms(const uint16_t* d_quantized, int64_t n_rows, int n_bins, float epsilon,
+                              float* d_hist, void* stream);
+
 /* ---- test hooks (not part of the product path) ----------------------------------------- */
 /* Evaluates the kernel's per-point inline function (csrc/nsc_point.h) on the HOST for
  * n_points points: row / col (or -1) and keep flag per point. It exists so that the CPU-only

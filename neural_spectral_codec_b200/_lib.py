@@ -75,6 +75,8 @@ SYMBOLS = {
     "nsc_wasserstein_cdf": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_wasserstein_query": (_I, [_VP, _I, _VP, _I64, _I, C.c_float, _VP, _VP, C.c_double, _VP, _I,
                                    _VP, _VP, _VP, _VP]),
+    "nsc_quantize_histograms": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
+    "nsc_dequantize_histograms": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_test_host_classify": (_I, [_VP, _I, _I64, _PP, _VP, _VP, _VP]),
     "nsc_test_row_mode": (_I, [_PP]),
 }
