@@ -6,6 +6,8 @@
 #include <string.h>
 
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include <cooperative_groups.h>
 
@@ -378,14 +380,44 @@ int device_info(DeviceInfo* out) {
     return NSC_OK;
 }
 
+// Raises the kernel's dynamic shared-memory limit when needed and returns its occupancy; both are
+// remembered per (kernel, device) so a steady-state launch makes no runtime query.
+struct KernelState {
+    const void* fn;
+    int device;
+    int smem_limit;                 // largest cudaFuncAttributeMaxDynamicSharedMemorySize set so far
+    std::vector<std::pair<int, int>> occupancy;   // (smem, blocks per SM)
+};
+
 template <typename K>
 int configure(K kernel, int smem, const DeviceInfo& di, int* blocks_per_sm) {
     if (smem > di.max_smem_optin) return NSC_ERR_BAD_PARAMS;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static std::mutex mu;
+    static std::vector<KernelState> states;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return record_cuda(e);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, kThreads, smem);
-    if (e != cudaSuccess) return record_cuda(e);
-    if (*blocks_per_sm < 1) return NSC_ERR_BAD_PARAMS;
+    std::lock_guard<std::mutex> lk(mu);
+    KernelState* ks = nullptr;
+    for (KernelState& s : states)
+        if (s.fn == (const void*)kernel && s.device == dev) ks = &s;
+    if (!ks) {
+        states.push_back(KernelState{(const void*)kernel, dev, 0, {}});
+        ks = &states.back();
+    }
+    if (smem > ks->smem_limit) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return record_cuda(e);
+        ks->smem_limit = smem;
+    }
+    if (blocks_per_sm) {
+        for (const auto& o : ks->occupancy)
+            if (o.first == smem) { *blocks_per_sm = o.second; return NSC_OK; }
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, kernel, kThreads, smem);
+        if (e != cudaSuccess) return record_cuda(e);
+        if (*blocks_per_sm < 1) return NSC_ERR_BAD_PARAMS;
+        ks->occupancy.emplace_back(smem, *blocks_per_sm);
+    }
     return NSC_OK;
 }
 
@@ -450,9 +482,8 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
         else
             kernel = poly ? encode_points_split_kernel<3, kRowPoly, kFeedLdg>
                           : encode_points_split_kernel<3, kRowSearch, kFeedLdg>;
-        if (L.total > di.max_smem_optin) return NSC_ERR_BAD_PARAMS;
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
-        if (e != cudaSuccess) return record_cuda(e);
+        st = configure(kernel, L.total, di, nullptr);
+        if (st != NSC_OK) return st;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_scans * csize));
         cfg.blockDim = dim3(kThreads);

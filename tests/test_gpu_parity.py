@@ -172,6 +172,38 @@ def test_cluster_split_equals_persistent_kernel():
     np.testing.assert_array_equal(sub3, full[7:10])
 
 
+def test_cuda_graph_capture_and_other_stream():
+    """The entry points only enqueue work on the caller's stream (no allocation, no sync), so a
+    call can be captured into a CUDA graph and replayed, or issued on a side stream."""
+    from neural_spectral_codec_b200 import synth
+    small = synth.SensorShape("s", 64, -24.8, 2.0, 500)
+    enc = make_encoder()
+    for n in (3, 180):                                   # cluster path and persistent path
+        pts, offs = synth.make_batch(small, 0, n, device="cuda")
+        want = enc.encode_points_batch(pts, offs)
+        out = torch.zeros_like(want)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            enc.encode_points_batch(pts, offs, out=out)
+        side.synchronize()
+        assert torch.equal(out, want)
+        out.zero_()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            enc.encode_points_batch(pts, offs, out=out)
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want)
+        pts2, _ = synth.make_batch(small, 1000, n, device="cuda")      # new content, same shapes
+        m = min(len(pts), len(pts2))
+        pts[:m] = pts2[:m]
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, enc.encode_points_batch(pts, offs))
+
+
 def test_ragged_batch_with_empty_and_filtered_scans():
     enc = make_encoder()
     cfg = orc.OracleConfig()
