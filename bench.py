@@ -206,7 +206,19 @@ def run_gpu_arm(args):
 
     sharded = None
     if world > 1:
-        sharded = ShardedEncoder(enc, world * n_scans, mode=args.gather)
+        try:
+            sharded = ShardedEncoder(enc, world * n_scans, mode=args.gather)
+        except Exception as exc:   # symmetric memory unavailable on this box: use the NCCL gather
+            if args.gather != "fused":
+                raise
+            print(f"[bench] fused gather unavailable ({type(exc).__name__}: {exc}); using nccl", file=sys.stderr)
+            ok = torch.tensor([0], device=dev)
+        else:
+            ok = torch.tensor([1], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # every rank must take the same path
+        if int(ok.item()) == 0 and args.gather == "fused":
+            args.gather = "nccl"
+            sharded = ShardedEncoder(enc, world * n_scans, mode="nccl")
     out = torch.empty((n_scans, enc.output_dim), dtype=torch.float32, device=dev)
 
     def step():
