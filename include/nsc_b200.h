@@ -134,6 +134,15 @@ int nsc_project_batch(const float* d_points, int point_stride, const int64_t* d_
                       int64_t point_origin, int n_scans, const nsc_params* p, int stage,
                       float* d_images, void* d_workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces RangeImageProjector.project(points, keep_intensity=True) (range_image.py:129-232):
+ * the range image and the intensity image (intensity of the closest point per pixel; the largest
+ * one when several points tie on the range, :217-226). 4-float points only. Not on the encoding
+ * path (spectral_encoder.py:217 passes keep_intensity=False); one packed 64-bit atomicMin on
+ * (range bits, ~intensity bits) per point. Both outputs: float32[n_scans * n_elevation * 360]. */
+int nsc_project_intensity_batch(const float* d_points, const int64_t* d_offsets,
+                                int64_t point_origin, int n_scans, const nsc_params* p,
+                                float* d_range_images, float* d_intensity_images, void* stream);
+
 /* Replaces SpectralEncoder.forward / encode_batch / encode_range_image
  * (spectral_encoder.py:160-204, :231-261): range images in, no projection and no
  * interpolation; rows are average-pooled to target_rows when they differ

@@ -41,8 +41,8 @@ class RangeImageProjector:
     """Spherical projection to an ``n_elevation x 360`` min-range image on the GPU.
 
     Mirrors ``RangeImageProjector`` (reference range_image.py:92-127 constructor,
-    :129-232 ``project``). Only the geometry branch (``keep_intensity=False``) exists: it is
-    the one on the encoder's path (spectral_encoder.py:217).
+    :129-232 ``project``). The encoder's path uses the geometry branch
+    (``keep_intensity=False``, spectral_encoder.py:217); the intensity image is a separate kernel.
     """
 
     def __init__(self, n_elevation: int = 64, n_azimuth: int = 360,
@@ -92,16 +92,36 @@ class RangeImageProjector:
         _lib.check(st, "nsc_project_batch")
         return out
 
+    def project_intensity_batch(self, points: torch.Tensor, offsets: torch.Tensor):
+        """Concatenated ``(sum N, 4)`` device scans -> ``(range images, intensity images)``, both
+        ``(B, n_elevation, 360)`` (reference range_image.py:216-230 for the second)."""
+        lib = _lib.load()
+        points, offsets, n_scans, stride = _check_batch(points, offsets)
+        if stride != 4:
+            raise ValueError("the intensity image needs (N, 4) points")
+        dev = points.device
+        shape = (n_scans, self.n_elevation, self.n_azimuth)
+        rng = torch.empty(shape, dtype=torch.float32, device=dev)
+        inten = torch.empty(shape, dtype=torch.float32, device=dev)
+        p = self._params()
+        with torch.cuda.device(dev):
+            st = lib.nsc_project_intensity_batch(points.data_ptr(), offsets.data_ptr(), 0, n_scans,
+                                                 C.byref(p), rng.data_ptr(), inten.data_ptr(),
+                                                 torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(st, "nsc_project_intensity_batch")
+        return rng, inten
+
     def project(self, points: np.ndarray, keep_intensity: bool = True):
-        """``project(points, keep_intensity=False) -> (range_image, None)`` as numpy, like the
-        reference (range_image.py:129-232)."""
-        if keep_intensity:
-            raise NotImplementedError(
-                "the intensity image is not on the encoding path (spectral_encoder.py:217 calls "
-                "project(points, keep_intensity=False)); pass keep_intensity=False")
+        """``project(points, keep_intensity) -> (range_image, intensity_image | None)`` as numpy,
+        like the reference (range_image.py:129-232): the intensity image exists only for 4-column
+        input with ``keep_intensity=True``."""
         if self.device is None or self.device.type != "cuda":
             raise _no_cpu("RangeImageProjector.project")
-        pts, offs = _host_scan_to_device(points, self.device)
+        a = _as_f32_points(points)
+        pts, offs = _host_scan_to_device(a, self.device)
+        if keep_intensity and a.shape[1] == 4:
+            rng, inten = self.project_intensity_batch(pts, offs)
+            return rng[0].cpu().numpy(), inten[0].cpu().numpy()
         img = self.project_batch(pts, offs)[0]
         return img.cpu().numpy(), None
 

@@ -97,6 +97,25 @@ def project(points: np.ndarray, cfg: OracleConfig) -> np.ndarray:
     return img
 
 
+def project_with_intensity(points: np.ndarray, cfg: OracleConfig):
+    """``RangeImageProjector.project(points, keep_intensity=True)`` (range_image.py:129-232): the
+    range image and, for 4-column input, the intensity image -- per pixel the largest intensity
+    among the points whose range equals the pixel's minimum, floored at the initial 0
+    (``np.maximum.at`` on zeros, :220-226). 3-column input -> ``(image, None)``."""
+    img = project(points, cfg)
+    p = np.asarray(points)
+    if p.shape[1] != 4:                                                          # :179-182
+        return img, None
+    s = spherical(points, cfg)
+    lin = s["row"] * cfg.n_azimuth + s["col"]
+    inten = p[s["kept"], 3]
+    flat = np.zeros(cfg.n_elevation * cfg.n_azimuth, dtype=np.float32)         # :220
+    closest = s["range"] == img.reshape(-1)[lin]                                 # :223
+    with np.errstate(invalid="ignore"):                                          # NaN intensities propagate
+        np.maximum.at(flat, lin[closest], inten[closest])                        # :226
+    return img, flat.reshape(cfg.n_elevation, cfg.n_azimuth)                     # :228
+
+
 # ------------------------------------------------------------------------ interpolation
 def interpolate_range_image(img: np.ndarray) -> np.ndarray:
     """``interpolate_range_image(img, 'linear')`` (range_image.py:15-89).

@@ -172,6 +172,30 @@ def test_cluster_split_equals_persistent_kernel():
     np.testing.assert_array_equal(sub3, full[7:10])
 
 
+def test_intensity_image_with_packed_64bit_min():
+    """project(points, keep_intensity=True): range image identical to the encoding path's, and the
+    intensity of the closest point per pixel (largest on range ties) as the reference computes it."""
+    g = np.load(os.path.join(GOLDEN_DIR, "intensity.npz"))
+    enc = make_encoder()
+    cfg = orc.OracleConfig()
+    for name in ("hdl64_small_shuffled", "beam128_small", "hdl32_small", "nonfinite", "intensity_ties"):
+        pts = g[name + "_points"]
+        r, i = enc.projector.project(pts)                       # keep_intensity defaults to True
+        r0, none = enc.projector.project(pts, keep_intensity=False)
+        assert none is None
+        np.testing.assert_array_equal(r, r0)
+        moved = (r != g[name + "_range"])
+        assert moved.sum() <= n_ambiguous(pts, cfg)
+        # wherever the pixel holds the same closest range as the reference, the intensity is identical
+        np.testing.assert_array_equal(i[~moved], g[name + "_intensity"][~moved])
+        s = orc.strip_ambiguous(pts, cfg)
+        rs, is_ = enc.projector.project(s, keep_intensity=True)
+        want_r, want_i = orc.project_with_intensity(s, cfg)
+        np.testing.assert_array_equal(rs, want_r)
+        np.testing.assert_array_equal(is_, want_i)
+    assert enc.projector.project(g["nonfinite_points"][:, :3])[1] is None
+
+
 def test_cuda_graph_capture_and_other_stream():
     """The entry points only enqueue work on the caller's stream (no allocation, no sync), so a
     call can be captured into a CUDA graph and replayed, or issued on a side stream."""

@@ -104,3 +104,16 @@ def test_strip_ambiguous_makes_assignment_robust():
     row = np.clip(np.floor((el - cfg.el_min) / (cfg.el_max - cfg.el_min) * 16).astype(int), 0, 15)
     np.testing.assert_array_equal(col, s["col"])
     np.testing.assert_array_equal(row, s["row"])
+
+
+def test_oracle_intensity_image_matches_reference_vectors():
+    g = np.load(os.path.join(GOLDEN_DIR, "intensity.npz"))
+    cfg = orc.OracleConfig()
+    for name in ("hdl64_small_shuffled", "beam128_small", "hdl32_small", "nonfinite", "intensity_ties"):
+        r, i = orc.project_with_intensity(g[name + "_points"], cfg)
+        if same_platform():
+            np.testing.assert_array_equal(r, g[name + "_range"])
+            np.testing.assert_array_equal(i, g[name + "_intensity"])
+        else:
+            assert (r != g[name + "_range"]).sum() <= 16
+    assert orc.project_with_intensity(g["nonfinite_points"][:, :3], cfg)[1] is None
