@@ -2,7 +2,7 @@
 
 Restates the reference's ``src/retrieval/wasserstein.py`` (batch distance :134-172, retriever
 :276-389) and the spatial filter of ``src/retrieval/two_stage_retrieval.py:145-202``. Only
-``tests/`` and the baseline legs of ``bench_retrieval.py`` may import it. Pinned by
+``tests/`` and the cpu_baseline leg of ``bench.py --workload retrieval`` may import it. Pinned by
 ``tests/golden/retrieval.npz`` (outputs of the unmodified reference, recorded by
 ``tests/golden/make_golden_retrieval.py``).
 """

@@ -4,7 +4,10 @@ gathered into the database replicated on every GPU (320 MB), with the checks of 
 every rank holds the same database bytes, and every 391st scan matches the CPU oracle.
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
-        --master-port 29513 tools/run_c5.py [--scans 100000] [--gather fused|nccl]
+        --master-port 29513 tests/multi_gpu_c5.py [--scans 100000] [--gather fused|nccl]
+
+Lives under tests/ because it checks against the oracle (test infrastructure); it is a script for
+a multi-GPU box, not collected by pytest.
 """
 import argparse
 import json
