@@ -39,12 +39,60 @@ struct EncodeArgs {
 //   kFeedCpAsync  per-thread ring of 16-byte cp.async copies (SASS LDGSTS): kCpDepth-1 stages in
 //                 flight per thread without holding registers; needs 16-byte points.
 //   kFeedLdg      plain vector loads into registers (3-float points; A/B with NSC_FEED=ldg).
-// A per-warp TMA bulk-copy ring (1.5 KB cp.async.bulk per stage) was measured at 0.47 of the
-// HBM roofline against 0.81 / 0.83 for these two (profiles/r1b_ncu_full_tma.txt) and removed.
-enum Feed { kFeedLdg = 0, kFeedCpAsync = 2 };
+// (An earlier per-WARP bulk-copy ring, 1.5 KB per copy, reached only 0.47 of the HBM roofline,
+// profiles/r1b_ncu_full_tma.txt; kFeedTma below copies whole 16 KB stages per CTA instead.)
+//   kFeedTma      the same ring filled by ONE elected thread with cp.async.bulk (SASS UBLKCP), a
+//                 whole 16 KB stage per copy, full/empty mbarriers per slot (NSC_FEED=tma).
+enum Feed { kFeedLdg = 0, kFeedCpAsync = 2, kFeedTma = 3 };
 constexpr int kDefaultFeed = kFeedCpAsync;
+constexpr int kTmaBarBytes = 128;   // 2 * kCpDepth mbarriers behind the ring
 __host__ __device__ constexpr int ring_bytes_of(int feed) {
-    return feed == kFeedCpAsync ? kCpRingBytes : 0;
+    return feed == kFeedCpAsync ? kCpRingBytes : feed == kFeedTma ? kCpRingBytes + kTmaBarBytes : 0;
+}
+
+// ---- mbarrier / bulk-copy (TMA) primitives ------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes,
+                                              uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+// full[s] at bars + 8 s (1 arrival: the producer's expect_tx), empty[s] at bars + 8 (kCpDepth + s)
+// (one arrival per consumer warp).
+__device__ __forceinline__ void tma_ring_init(unsigned char* ring) {
+    if (threadIdx.x == 0) {
+        const uint32_t bars = (uint32_t)__cvta_generic_to_shared(ring) + kCpRingBytes;
+        for (int s = 0; s < kCpDepth; ++s) {
+            mbar_init(bars + 8 * s, 1);
+            mbar_init(bars + 8 * (kCpDepth + s), kWarps - 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -106,9 +154,55 @@ __device__ __forceinline__ void project_point(float x, float y, float z, const D
 template <int STRIDE, int ROWMODE, int FEED>
 __device__ __forceinline__ void point_pass(const float* __restrict__ points, long long beg, int n,
                                            const DeviceParams& dp, uint32_t img_biased,
-                                           unsigned char* ring) {
+                                           unsigned char* ring, uint32_t& g_stage) {
     const int tid = threadIdx.x;
-    if (FEED == kFeedCpAsync) {
+    if (FEED == kFeedTma) {
+        // The last warp is the producer: its lane 0 keeps kCpDepth - 1 whole-stage bulk copies in
+        // flight; the other kWarps - 1 warps consume. Stage g of this CTA (counted across scans)
+        // lives in slot g % kCpDepth, full-barrier parity (g / kCpDepth) & 1; a slot is refilled
+        // once every consumer warp has arrived on its empty barrier.
+        constexpr int kConsumers = kThreads - 32;
+        constexpr int kStagePoints = kCpPts * kConsumers;
+        constexpr int kSlotBytes = kCpPts * kThreads * 16;
+        const float4* p4 = reinterpret_cast<const float4*>(points) + beg;
+        const uint32_t ring_u = smem_u32(ring), bars = ring_u + kCpRingBytes;
+        const int n_iter = (n + kStagePoints - 1) / kStagePoints;
+        const uint32_t g0 = g_stage;
+        if (tid >= kConsumers) {
+            if (tid == kConsumers) {
+                for (int it = 0; it < n_iter; ++it) {
+                    const uint32_t g = g0 + it, slot = g % kCpDepth;
+                    if (g >= kCpDepth) mbar_wait(bars + 8 * (kCpDepth + slot), ((g / kCpDepth) + 1) & 1);
+                    const uint32_t bytes = (uint32_t)min(kStagePoints, n - it * kStagePoints) * 16u;
+                    mbar_expect_tx(bars + 8 * slot, bytes);
+                    bulk_copy_g2s(ring_u + slot * kSlotBytes, p4 + (long long)it * kStagePoints, bytes,
+                                  bars + 8 * slot);
+                }
+            }
+        } else {
+            for (int it = 0; it < n_iter; ++it) {
+                const uint32_t g = g0 + it, slot = g % kCpDepth;
+                mbar_wait(bars + 8 * slot, (g / kCpDepth) & 1);
+                float4 v[kCpPts];
+#pragma unroll
+                for (int u = 0; u < kCpPts; ++u)
+                    v[u] = lds128(ring_u + slot * kSlotBytes + (u * kConsumers + tid) * 16);
+                if ((it + 1) * kStagePoints <= n) {
+#pragma unroll
+                    for (int u = 0; u < kCpPts; ++u)
+                        project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < kCpPts; ++u)
+                        project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased,
+                                               it * kStagePoints + u * kConsumers + tid < n);
+                }
+                __syncwarp();
+                if ((tid & 31) == 0) mbar_arrive(bars + 8 * (kCpDepth + slot));
+            }
+        }
+        g_stage = g0 + (uint32_t)n_iter;
+    } else if (FEED == kFeedCpAsync) {
         // Each thread streams its own points through a private kCpDepth-deep shared-memory
         // ring of 16-byte cp.async copies. No cross-thread barrier is needed: a thread only
         // reads what it copied itself. Stage `it` holds points it*kStagePoints +
@@ -246,17 +340,22 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
     const int n_pix = dp.E * kPitch;
 
     init_twiddles(S.tw);
+    uint32_t g_stage = 0;
+    if (FEED == kFeedTma) tma_ring_init(smem_raw + L.ring_off);
 
     for (;;) {
         __syncthreads();
         if (tid == 0) s_scan = (int)atomicAdd(a.counter, 1u);
         for (int i = tid; i < n_pix; i += kThreads) img[i] = kInfBits;
+        // The ring doubles as FFT scratch in the tail: every thread orders its generic-proxy
+        // writes before the barrier, the bulk copies (async proxy) are issued after it.
+        if (FEED == kFeedTma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
         const int scan = s_scan;
         if (scan >= a.n_scans) break;
         const long long beg = a.offsets[scan] - a.origin;
         const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
-        point_pass<STRIDE, ROWMODE, FEED>(a.points, beg, n, dp, img_biased, smem_raw + L.ring_off);
+        point_pass<STRIDE, ROWMODE, FEED>(a.points, beg, n, dp, img_biased, smem_raw + L.ring_off, g_stage);
         __syncthreads();
         finish_scan(a, dp, S, scan);
     }
@@ -283,13 +382,15 @@ encode_points_split_kernel(const __grid_constant__ EncodeArgs a, const __grid_co
     const int scan = blockIdx.x / csize;      // grid = n_scans * cluster size
 
     if (rank == 0) init_twiddles(S.tw);
+    uint32_t g_stage = 0;
+    if (FEED == kFeedTma) tma_ring_init(smem_raw + L.ring_off);
     for (int i = tid; i < n_pix; i += kThreads) img[i] = kInfBits;
     __syncthreads();
     const long long beg = a.offsets[scan] - a.origin;
     const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
     const int per = (n + (int)csize - 1) / (int)csize;
     const int lo = min(n, (int)rank * per), hi = min(n, lo + per);
-    point_pass<STRIDE, ROWMODE, FEED>(a.points, beg + lo, hi - lo, dp, img_biased, smem_raw + L.ring_off);
+    point_pass<STRIDE, ROWMODE, FEED>(a.points, beg + lo, hi - lo, dp, img_biased, smem_raw + L.ring_off, g_stage);
     cluster.sync();                           // every partial image is complete
     if (rank == 0) {
         for (int i = tid; i < n_pix; i += kThreads) {
@@ -454,7 +555,8 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     static const int feed_override = [] {
         const char* e = getenv("NSC_FEED");
         if (!e) return -1;
-        return strcmp(e, "ldg") == 0 ? (int)kFeedLdg : strcmp(e, "cpasync") == 0 ? (int)kFeedCpAsync : -1;
+        return strcmp(e, "ldg") == 0 ? (int)kFeedLdg : strcmp(e, "cpasync") == 0 ? (int)kFeedCpAsync
+               : strcmp(e, "tma") == 0 ? (int)kFeedTma : -1;
     }();
     int feed = feed_override >= 0 ? feed_override : kDefaultFeed;
     if (stride != 4) feed = kFeedLdg;
@@ -473,7 +575,10 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     void (*kernel)(const EncodeArgs, const DeviceParams) = nullptr;
     const bool poly = dp.row_mode == kRowPoly;
     if (csize > 1) {
-        if (feed == kFeedCpAsync)
+        if (feed == kFeedTma)
+            kernel = poly ? encode_points_split_kernel<4, kRowPoly, kFeedTma>
+                          : encode_points_split_kernel<4, kRowSearch, kFeedTma>;
+        else if (feed == kFeedCpAsync)
             kernel = poly ? encode_points_split_kernel<4, kRowPoly, kFeedCpAsync>
                           : encode_points_split_kernel<4, kRowSearch, kFeedCpAsync>;
         else if (stride == 4)
@@ -498,7 +603,10 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
         cfg.numAttrs = 1;
         return record_cuda(cudaLaunchKernelEx(&cfg, kernel, a, dp));
     }
-    if (feed == kFeedCpAsync) {
+    if (feed == kFeedTma) {
+        kernel = poly ? encode_points_kernel<4, kRowPoly, kFeedTma>
+                      : encode_points_kernel<4, kRowSearch, kFeedTma>;
+    } else if (feed == kFeedCpAsync) {
         kernel = poly ? encode_points_kernel<4, kRowPoly, kFeedCpAsync>
                       : encode_points_kernel<4, kRowSearch, kFeedCpAsync>;
     } else if (stride == 4) {

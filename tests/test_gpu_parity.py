@@ -360,3 +360,51 @@ def test_error_statuses_through_the_abi():
     bl[5] = 49
     assert call(l=bl) == -5
     torch.cuda.synchronize()
+
+
+def test_plain_c_caller_runs():
+    """examples/c_abi_demo.c (gcc -std=c99, host buffers, pipeline entry points)."""
+    import subprocess
+    import tempfile
+    from conftest import ROOT
+    from neural_spectral_codec_b200 import _lib
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "demo")
+        subprocess.run(["gcc", "-std=c99", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + os.path.dirname(_lib.LIB_PATH),
+                        "-lnsc_b200", "-lm", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-o", exe], check=True)
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert r.stdout.count("descriptor sum 1.0000") + r.stdout.count("descriptor sum 0.9999") == 2, r.stdout
+
+
+@pytest.mark.parametrize("feed", ["tma", "ldg"])
+def test_alternative_feeds_give_the_same_bits(feed, tmp_path):
+    """The point pass can be fed by cp.async (default), by whole-stage TMA bulk copies with a
+    producer warp, or by plain vector loads (NSC_FEED, read once per process): same descriptors."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from neural_spectral_codec_b200 import synth
+    small = synth.SensorShape("s", 64, -24.8, 2.0, 700)
+    enc = make_encoder()
+    want = {}
+    for n in (2, 170):                                     # cluster path and persistent path
+        pts, offs = synth.make_batch(small, 5, n, device="cuda")
+        want[n] = enc.encode_points_batch(pts, offs).cpu().numpy()
+        np.save(tmp_path / f"want{n}.npy", want[n])
+    code = f"""
+import sys, numpy as np, torch
+sys.path.insert(0, {ROOT!r})
+from neural_spectral_codec_b200 import SpectralEncoder, synth
+small = synth.SensorShape("s", 64, -24.8, 2.0, 700)
+enc = SpectralEncoder(n_elevation=16, target_elevation_bins=16).to("cuda")
+for n in (2, 170):
+    pts, offs = synth.make_batch(small, 5, n, device="cuda")
+    got = enc.encode_points_batch(pts, offs).cpu().numpy()
+    assert np.array_equal(got, np.load(r"{tmp_path}/want%d.npy" % n)), n
+print("same")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, NSC_FEED=feed), timeout=600)
+    assert r.returncode == 0 and "same" in r.stdout, r.stderr[-2000:]

@@ -206,3 +206,19 @@ def test_range_thresholds_are_exact_preimages(lib):
     _, _, keep = host_classify(lib, pts)
     rng = np.sqrt(pts[:, 0] * pts[:, 0])
     np.testing.assert_array_equal(keep, (rng >= f(1.0)) & (rng <= f(80.0)))
+
+
+def test_header_is_plain_c_and_the_c_demo_links(lib, tmp_path):
+    """include/nsc_b200.h must be usable from C (the boundary is a C ABI, not C++): compile the
+    example caller with gcc -std=c99 and link it against the shared library."""
+    import subprocess
+    exe = tmp_path / "c_abi_demo"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L" + os.path.dirname(_lib.LIB_PATH), "-lnsc_b200",
+           "-lm", "-Wl,-rpath," + os.path.dirname(_lib.LIB_PATH), "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # without a GPU the demo must fail with the library's CUDA status, not crash
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "CUDA runtime error" in r.stderr
