@@ -312,9 +312,21 @@ def run_gpu_arm(args):
         cores = os.cpu_count() or 1
         per_core = 24
         v, n = cpu_oracle_throughput(per_core, cores)
+        # the reference's native call pattern: one process looping encode_points (pipeline.py:336-354)
+        from oracle import nsc_oracle as orc
+        cfg = orc.OracleConfig()
+        host_scans = [points[int(offsets[i]):int(offsets[i + 1])].cpu().numpy() for i in range(12)]
+        orc.encode_points(host_scans[0], cfg)
+        t0 = time.perf_counter()
+        for s_ in host_scans:
+            orc.encode_points(s_, cfg)
+        single = len(host_scans) / (time.perf_counter() - t0)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{n} HDL-64 scans ({per_core} per core), oracle/nsc_oracle.py, "
-                                  "one single-threaded process per core"}
+                                  "one single-threaded process per core",
+                        "single_process_value": single,
+                        "single_process_sample": f"{len(host_scans)} scans in one process, torch threads = "
+                                                 f"{torch.get_num_threads()} (the reference's per-scan loop)"}
 
     if rank == 0:
         line = {

@@ -96,6 +96,20 @@ def test_stripped_cloud_is_bit_exact(name):
     assert_descriptor(enc.encode_points(pts).cpu().numpy(), orc.encode_points(pts, cfg).numpy())
 
 
+def test_gpu_error_against_float64_is_no_worse_than_the_reference(name="hdl64_full"):
+    """both float32 results are compared with a float64 evaluation of the same
+    spectrum; the CUDA path must not be further from it than the reference's own float32 path."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    cfg = orc.OracleConfig()
+    pts = orc.strip_ambiguous(g["points"], cfg)
+    truth = orc.descriptor_f64(pts, cfg)
+    ref = orc.encode_points(pts, cfg).numpy().astype(np.float64)
+    got = make_encoder().encode_points(pts).cpu().numpy().astype(np.float64)
+    err_ref, err_gpu = np.abs(ref - truth).max(), np.abs(got - truth).max()
+    assert err_gpu <= 2.0 * err_ref + 1e-9, (err_gpu, err_ref)
+    assert np.linalg.norm(got - truth) <= 2.0 * np.linalg.norm(ref - truth) + 1e-9
+
+
 def test_interpolate_entry_matches_reference_vectors():
     from neural_spectral_codec_b200 import interpolate_range_image
     for name in POINT_CASES:
