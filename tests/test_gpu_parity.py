@@ -422,3 +422,63 @@ print("same")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                        env=dict(os.environ, NSC_FEED=feed), timeout=600)
     assert r.returncode == 0 and "same" in r.stdout, r.stderr[-2000:]
+
+
+def random_cloud(rng, n, el=(-0.42, 0.03)):
+    az = rng.uniform(-np.pi, np.pi, n)
+    e = rng.uniform(el[0], el[1], n)
+    r = rng.uniform(1.5, 70, n)
+    return np.stack([r * np.cos(e) * np.cos(az), r * np.cos(e) * np.sin(az), r * np.sin(e),
+                     rng.random(n)], 1).astype(np.float32)
+
+
+def test_scan_sizes_around_the_ring_stage_boundaries():
+    """Point counts at and around multiples of the 1024-point cp.async stage (and of the 4-stage
+    unrolled trip), through the persistent kernel (large batch) and the cluster kernel (slices)."""
+    rng = np.random.default_rng(17)
+    sizes = [0, 1, 2, 31, 511, 512, 513, 1023, 1024, 1025, 2047, 2048, 2049, 3072, 4095, 4096, 4097,
+             6143, 6144, 6145, 7167, 7168, 7169, 8191, 8192, 8193, 10240, 12289, 16384, 20001]
+    sizes = sizes + [int(x) for x in rng.integers(1, 9000, 60)]            # 90 scans -> persistent kernel
+    scans = [random_cloud(rng, n) for n in sizes]
+    offs = np.cumsum([0] + sizes)
+    pts = torch.from_numpy(np.concatenate(scans)).cuda()
+    enc = make_encoder()
+    cfg = orc.OracleConfig()
+    full = enc.encode_points_batch(pts, torch.from_numpy(offs)).cpu().numpy()
+    imgs = enc.projector.project_batch(pts, torch.from_numpy(offs)).cpu().numpy()
+    for i in range(30):
+        st = orc.strip_ambiguous(scans[i], cfg)
+        if len(st) == len(scans[i]):
+            np.testing.assert_array_equal(imgs[i], orc.project(scans[i], cfg))
+        assert np.abs(full[i] - orc.encode_points(scans[i], cfg).numpy()).max() < 1e-4, sizes[i]
+    for first, count in ((3, 1), (8, 7), (10, 20)):                          # cluster sizes 8, 8, 4
+        sub = enc.encode_points_batch(pts[offs[first]:offs[first + count]],
+                                      torch.from_numpy(offs[first:first + count + 1] - offs[first]))
+        np.testing.assert_array_equal(sub.cpu().numpy(), full[first:first + count])
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_elevation=32, target_elevation_bins=32),                  # 16 complex FFTs: two batches of 8
+    dict(n_elevation=64, target_elevation_bins=64, n_bins=20),
+    dict(n_elevation=16, target_elevation_bins=5),                   # odd target, pooled 16 -> 5
+    dict(n_elevation=40, target_elevation_bins=16, n_bins=30, alpha=1.3),
+    dict(n_elevation=16, target_elevation_bins=16, n_bins=181, alpha=0.7),
+    dict(n_elevation=8, target_elevation_bins=16),                   # fewer rows than targets
+    dict(n_elevation=1, target_elevation_bins=1, n_bins=7),
+])
+def test_other_encoder_geometries_against_the_oracle(kw):
+    rng = np.random.default_rng(5)
+    enc = make_encoder(**kw)
+    okw = dict(kw)
+    cfg = orc.OracleConfig(**okw)
+    scans = [random_cloud(rng, n) for n in (9000, 300, 4000)] + [random_cloud(rng, 2500) for _ in range(80)]
+    sizes = [len(s) for s in scans]
+    offs = np.cumsum([0] + sizes)
+    pts = torch.from_numpy(np.concatenate(scans)).cuda()
+    d = enc.encode_points_batch(pts, torch.from_numpy(offs)).cpu().numpy()      # persistent kernel
+    assert d.shape == (len(scans), cfg.output_dim)
+    for i in (0, 1, 2, 40, 82):
+        st = orc.strip_ambiguous(scans[i], cfg)
+        got = enc.encode_points(st).cpu().numpy()                               # cluster kernel
+        assert_descriptor(got, orc.encode_points(st, cfg).numpy())
+        assert np.abs(d[i] - orc.encode_points(scans[i], cfg).numpy()).max() < 2e-4
