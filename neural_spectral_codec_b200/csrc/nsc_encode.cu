@@ -125,6 +125,15 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 __device__ __forceinline__ void scatter_min(uint32_t img_biased, uint32_t row_b, uint32_t col_b,
                                             uint32_t key) {
     const uint32_t addr = row_b * (uint32_t)(kPitch * 4) + (col_b * 4u + img_biased);
+#ifdef NSC_DEBUG_BOUNDS
+    // self-check build (compute-sanitizer is closed on this pool): the pixel must lie inside the image
+    {
+        const uint32_t r = row_b - kFloorBias, c = col_b - kFloorBias;
+        if (r >= (uint32_t)NSC_MAX_ELEVATION || c > (uint32_t)kAz ||
+            addr - (img_biased + kFloorBias * (uint32_t)(kPitch * 4 + 4)) != (r * kPitch + c) * 4u)
+            __trap();
+    }
+#endif
 #if NSC_PRECHECK
     uint32_t cur;
     asm("ld.shared.u32 %0, [%1];" : "=r"(cur) : "r"(addr));
