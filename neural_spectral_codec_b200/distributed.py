@@ -15,8 +15,6 @@ itself always needs a CUDA device.
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
-
 import torch
 import torch.distributed as dist
 

@@ -22,7 +22,7 @@ Beyond the reference surface:
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple, Union
+from typing import Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch

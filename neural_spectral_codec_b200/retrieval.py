@@ -14,7 +14,6 @@ there is no CPU path.
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Tuple, Union
 
 import numpy as np

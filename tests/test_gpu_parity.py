@@ -7,7 +7,6 @@ Tolerances (BASELINE.json north_star):
   * interpolation, keep/drop, freq->bin table: bit-exact;
   * descriptor: allclose(rtol=1e-4, atol=1e-7) and ||gpu - ref||_2 <= 1e-5 ||ref||_2.
 """
-import glob
 import os
 
 import numpy as np

@@ -1,5 +1,4 @@
 """Pin oracle/ to the vectors recorded from the unmodified reference (tests/golden/)."""
-import glob
 import os
 
 import numpy as np

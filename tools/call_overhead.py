@@ -21,7 +21,6 @@ for _ in range(n):
     enc.encode_points_batch(pts, offs, out=out)
 torch.cuda.synchronize()
 print(f"encode_points_batch: {(time.perf_counter() - t0) / n * 1e6:.1f} us per call (1 tiny scan, device-resident)")
-import numpy as np
 host = synth.make_scan(synth.HDL64, 0).numpy()
 for _ in range(20):
     enc.encode_points(host)
