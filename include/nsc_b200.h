@@ -172,6 +172,15 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
                         const int64_t* h_offsets, int n_scans, const nsc_params* p,
                         const int32_t* h_lut, float* h_out);
 
+/* The same for scans that live in SEPARATE host arrays, as the reference's loaders hand them
+ * out one np.fromfile() at a time (kitti_loader.py:100-115) -- the loop of pipeline.py:336-354
+ * without concatenating first. h_scans[i] points to h_counts[i] points of point_stride floats
+ * (pageable memory is fine: chunks are gathered into pinned staging by a few host threads while
+ * the previous chunk is on the wire). h_out: float32[n_scans * target_rows * n_bins]. */
+int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, const int64_t* h_counts,
+                              int point_stride, int n_scans, const nsc_params* p,
+                              const int32_t* h_lut, float* h_out);
+
 /* ---- stage-1 retrieval over the descriptor database (first "next" row) ---- */
 /* Normalised CDF rows of a block of database histograms: cdf = cumsum(h / (sum h + eps)) where
  * sum h > eps, cumsum(h) otherwise -- the database half of wasserstein_distance_batch_torch

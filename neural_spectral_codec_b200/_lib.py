@@ -73,6 +73,7 @@ SYMBOLS = {
     "nsc_pipeline_create": (_I, [_I64, _I, _I, C.POINTER(_VP)]),
     "nsc_pipeline_destroy": (None, [_VP]),
     "nsc_pipeline_encode": (_I, [_VP, _VP, _I, _VP, _I, _PP, _VP, _VP]),
+    "nsc_pipeline_encode_scans": (_I, [_VP, _VP, _VP, _I, _I, _PP, _VP, _VP]),
     "nsc_wasserstein_cdf": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_wasserstein_query": (_I, [_VP, _I, _VP, _I64, _I, C.c_float, _VP, _VP, C.c_double, _VP, _I,
                                    _VP, _VP, _VP, _VP]),

@@ -2,6 +2,7 @@
 #include <string.h>
 
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "nsc_point.h"
@@ -127,6 +128,9 @@ struct nsc_pipeline {
         long long* d_offsets;
         float* d_out;
         unsigned* d_ws;
+        float* h_stage;        // pinned staging of one chunk (nsc_pipeline_encode_scans), lazy
+        long long* h_offsets;  // pinned chunk offsets
+        float* h_out;          // pinned chunk descriptors
         bool busy;
     } slot[4];
 };
@@ -146,6 +150,9 @@ void nsc_pipeline_destroy(nsc_pipeline* pl) {
         if (s.d_offsets) cudaFree(s.d_offsets);
         if (s.d_out) cudaFree(s.d_out);
         if (s.d_ws) cudaFree(s.d_ws);
+        if (s.h_stage) cudaFreeHost(s.h_stage);
+        if (s.h_offsets) cudaFreeHost(s.h_offsets);
+        if (s.h_out) cudaFreeHost(s.h_out);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -248,6 +255,118 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
         nsc_pipeline::Slot& s = pl->slot[i];
         if ((e = cudaStreamSynchronize(s.stream)) != cudaSuccess && st == NSC_OK) st = record_cuda(e);
         s.busy = false;
+    }
+    cudaSetDevice(prev);
+    return st;
+}
+
+// Copies scans [first, last) into the pinned staging buffer with a few host threads (a single
+// memcpy stream cannot keep up with PCIe 5 from pageable memory).
+static void stage_scans(float* dst, const float* const* h_scans, const int64_t* h_counts, int first,
+                        int last, int stride, long long* offs_out) {
+    std::vector<size_t> start(last - first + 1, 0);
+    for (int i = first; i < last; ++i) start[i - first + 1] = start[i - first] + (size_t)h_counts[i];
+    for (int i = first; i <= last; ++i) offs_out[i - first] = (long long)start[i - first];
+    const size_t total_bytes = start[last - first] * stride * 4;
+    unsigned hw = std::thread::hardware_concurrency();
+    int n_thr = (int)(total_bytes >> 22);                 // one thread per 4 MiB, at most 12
+    if (n_thr > 12) n_thr = 12;
+    if (hw && n_thr > (int)hw) n_thr = (int)hw;
+    if (n_thr < 1) n_thr = 1;
+    auto work = [&](int t) {
+        // thread t copies the byte range [t, t+1) * total / n_thr, walking the scans it overlaps
+        const size_t lo = total_bytes * t / n_thr, hi = total_bytes * (t + 1) / n_thr;
+        for (int i = first; i < last; ++i) {
+            const size_t b0 = start[i - first] * stride * 4, b1 = start[i - first + 1] * stride * 4;
+            const size_t c0 = b0 > lo ? b0 : lo, c1 = b1 < hi ? b1 : hi;
+            if (c0 < c1)
+                memcpy((char*)dst + c0, (const char*)h_scans[i] + (c0 - b0), c1 - c0);
+        }
+    };
+    if (n_thr == 1) { work(0); return; }
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_thr; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+}
+
+int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, const int64_t* h_counts,
+                              int point_stride, int n_scans, const nsc_params* p,
+                              const int32_t* h_lut, float* h_out) {
+    if (!pl) return NSC_ERR_NULL_POINTER;
+    DeviceParams dp;
+    int st = make_device_params(p, h_lut, &dp);
+    if (st != NSC_OK) return st;
+    if (n_scans < 0) return NSC_ERR_BAD_COUNT;
+    if (point_stride != 3 && point_stride != 4) return NSC_ERR_BAD_STRIDE;
+    if (n_scans == 0) return NSC_OK;
+    if (!h_scans || !h_counts || !h_out) return NSC_ERR_NULL_POINTER;
+    for (int i = 0; i < n_scans; ++i) {
+        if (h_counts[i] < 0) return NSC_ERR_BAD_OFFSETS;
+        if (h_counts[i] > 0 && !h_scans[i]) return NSC_ERR_NULL_POINTER;
+        if (h_counts[i] > pl->max_chunk_points) return NSC_ERR_WORKSPACE;
+    }
+    const int D = dp.T * dp.n_bins;
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return record_cuda(e);
+    e = cudaSetDevice(pl->device);
+    if (e != cudaSuccess) return record_cuda(e);
+
+    struct Pending { int first, count; };
+    Pending pending[4] = {};
+    auto retire = [&](int k) -> int {      // wait for slot k and hand its descriptors to the caller
+        nsc_pipeline::Slot& s = pl->slot[k];
+        if (!s.busy) return NSC_OK;
+        cudaError_t er = cudaEventSynchronize(s.done);
+        if (er != cudaSuccess) return record_cuda(er);
+        memcpy(h_out + (size_t)pending[k].first * D, s.h_out, (size_t)pending[k].count * D * 4);
+        s.busy = false;
+        return NSC_OK;
+    };
+    int first = 0, k = 0;
+    while (first < n_scans && st == NSC_OK) {
+        int last = first;
+        int64_t np = 0;
+        while (last < n_scans && last - first < pl->max_chunk_scans && np + h_counts[last] <= pl->max_chunk_points)
+            np += h_counts[last++];
+        const int slot_i = k % pl->n_buffers;
+        nsc_pipeline::Slot& s = pl->slot[slot_i];
+        if ((st = retire(slot_i)) != NSC_OK) break;
+        if (!s.h_stage) {
+            if ((e = cudaHostAlloc(&s.h_stage, (size_t)pl->max_chunk_points * 16, cudaHostAllocDefault)) != cudaSuccess ||
+                (e = cudaHostAlloc(&s.h_offsets, (size_t)(kMaxChunkScans + 1) * 8, cudaHostAllocDefault)) != cudaSuccess ||
+                (e = cudaHostAlloc(&s.h_out, (size_t)kMaxChunkScans * kMaxDescriptor * 4, cudaHostAllocDefault)) != cudaSuccess) {
+                st = record_cuda(e);
+                break;
+            }
+        }
+        const int ns = last - first;
+        stage_scans(s.h_stage, h_scans, h_counts, first, last, point_stride, s.h_offsets);
+        if ((e = cudaMemcpyAsync(s.d_points, s.h_stage, (size_t)np * point_stride * 4,
+                                 cudaMemcpyHostToDevice, s.stream)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(s.d_offsets, s.h_offsets, (size_t)(ns + 1) * 8, cudaMemcpyHostToDevice,
+                                 s.stream)) != cudaSuccess) {
+            st = record_cuda(e);
+            break;
+        }
+        st = launch_encode(s.d_points, point_stride, s.d_offsets, 0, ns, dp, s.d_out, nullptr, 0, nullptr, 0,
+                           0, s.d_ws, s.stream);
+        if (st != NSC_OK) break;
+        if ((e = cudaMemcpyAsync(s.h_out, s.d_out, (size_t)ns * D * 4, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess ||
+            (e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) {
+            st = record_cuda(e);
+            break;
+        }
+        s.busy = true;
+        pending[slot_i].first = first;
+        pending[slot_i].count = ns;
+        first = last;
+        ++k;
+    }
+    for (int i = 0; i < pl->n_buffers; ++i) {
+        if (st == NSC_OK) st = retire(i);
+        else { cudaStreamSynchronize(pl->slot[i].stream); pl->slot[i].busy = false; }
     }
     cudaSetDevice(prev);
     return st;

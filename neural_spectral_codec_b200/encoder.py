@@ -285,6 +285,7 @@ class SpectralEncoder(nn.Module):
         """
         lib = _lib.load()
         dev = self._cuda_device("encode_scans")
+        arrs = None
         if isinstance(scans, tuple) and len(scans) == 2 and np.ndim(scans[1]) == 1:
             pts = scans[0]
             if isinstance(pts, torch.Tensor):
@@ -301,7 +302,6 @@ class SpectralEncoder(nn.Module):
                 arrs = [np.ascontiguousarray(a[:, :3]) for a in arrs]
             offs = np.zeros(len(arrs) + 1, np.int64)
             np.cumsum([a.shape[0] for a in arrs], out=offs[1:])
-            pts = np.concatenate(arrs, 0) if arrs else np.zeros((0, 4), np.float32)
         n_scans = offs.shape[0] - 1
         if out is None:
             out = np.empty((n_scans, self.output_dim), np.float32)
@@ -319,6 +319,13 @@ class SpectralEncoder(nn.Module):
             self._pipeline, self._pipeline_key = h, key
         p = self._params()
         lut = self.freq_to_bin()
+        if arrs is not None:   # separate host arrays: gathered into pinned staging inside the library
+            ptrs = (C.c_void_p * n_scans)(*[a.ctypes.data for a in arrs])
+            counts = np.diff(offs)
+            st = lib.nsc_pipeline_encode_scans(self._pipeline, ptrs, counts.ctypes.data, arrs[0].shape[1],
+                                               n_scans, C.byref(p), lut.ctypes.data, out.ctypes.data)
+            _lib.check(st, "nsc_pipeline_encode_scans")
+            return out
         st = lib.nsc_pipeline_encode(self._pipeline, pts.ctypes.data, pts.shape[1], offs.ctypes.data,
                                      n_scans, C.byref(p), lut.ctypes.data, out.ctypes.data)
         _lib.check(st, "nsc_pipeline_encode")
