@@ -307,22 +307,13 @@ __device__ __forceinline__ void finish_scan(const EncodeArgs& a, const DevicePar
                                             const TailSmem& S, int scan) {
     const int tid = threadIdx.x;
     const int D = dp.T * dp.n_bins;
-    const uint32_t* img = reinterpret_cast<const uint32_t*>(S.img);
-    // bits of min s -> range = sqrt_rn(s); empty -> 0 (range_image.py:162,:214). Column 360
-    // (azimuth exactly 2 pi) belongs to column 0.
-    for (int i = tid; i < dp.E * kAz; i += kThreads) {
-        const int r = i / kAz, c = i - r * kAz;
-        uint32_t b = img[r * kPitch + c];
-        if (c == 0) b = min(b, img[r * kPitch + kAz]);
-        const float v = key_is_empty(b, dp) ? 0.0f : __fsqrt_rn(__uint_as_float(b));
-        S.img[r * kPitch + c] = v;
-        if (a.img_out && a.stage == NSC_STAGE_PROJECTED)
-            a.img_out[(long long)scan * dp.E * kAz + i] = v;
-    }
-    __syncthreads();
-    build_masks(S, dp.E);
-    __syncthreads();
-    interpolate_and_fill(S, dp.E, dp.interpolate != 0);
+    // bits of min s -> range = sqrt_rn(s); empty -> 0 (range_image.py:162,:214); masks; hole
+    // interpolation; empty-row indirection
+    float* stage0 = (a.img_out && a.stage == NSC_STAGE_PROJECTED)
+                        ? a.img_out + (long long)scan * dp.E * kAz : nullptr;
+    rows_to_filled<true>(S, dp.E, dp.interpolate != 0, stage0, [&dp](uint32_t key) {
+        return key_is_empty(key, dp) ? 0.0f : __fsqrt_rn(__uint_as_float(key));
+    });
     if (a.img_out && a.stage == NSC_STAGE_INTERPOLATED) {
         for (int i = tid; i < dp.E * kAz; i += kThreads) {
             const int r = i / kAz, c = i - r * kAz;
@@ -456,9 +447,7 @@ interpolate_kernel(const float* __restrict__ in, int n_images, int rows, float* 
             S.img[r * kPitch + c] = src[i];
         }
         __syncthreads();
-        build_masks(S, rows);
-        __syncthreads();
-        interpolate_and_fill(S, rows, true);
+        rows_to_filled<false>(S, rows, true, nullptr, [](uint32_t) { return 0.0f; });
         float* dst = out + (long long)im * rows * kAz;
         for (int i = threadIdx.x; i < rows * kAz; i += kThreads) {
             const int r = i / kAz, c = i - r * kAz;

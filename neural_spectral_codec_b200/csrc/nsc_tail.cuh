@@ -87,22 +87,6 @@ __device__ __forceinline__ void init_twiddles(float2* tw) {
     }
 }
 
-// mask / nvalid from the float image (valid <=> value > 0, range_image.py:35).
-__device__ __forceinline__ void build_masks(const TailSmem& S, int rows) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < rows; r += kWarps) {
-        int cnt = 0;
-        for (int w = 0; w < kMaskWords; ++w) {
-            const int c = w * 32 + lane;
-            const bool valid = (c < kAz) && (S.img[r * kPitch + c] > 0.0f);
-            const uint32_t m = __ballot_sync(0xffffffffu, valid);
-            cnt += __popc(m);
-            if (lane == 0) S.mask[r * kMaskWords + w] = m;
-        }
-        if (lane == 0) S.nvalid[r] = cnt;
-    }
-}
-
 // Nearest valid column strictly left / right of x on the circular row; the returned position
 // is unwrapped (left in (x-360, x), right in (x, x+360)), as np.interp sees it on the tiled
 // abscissa (range_image.py:55-64). Requires at least one valid bit in the row.
@@ -125,17 +109,43 @@ __device__ __forceinline__ int next_valid(const uint32_t* m, int x) {
     return off + w * 32 + __ffs(bits) - 1;
 }
 
-// interpolate_range_image(img, 'linear') in place (range_image.py:33-64 and :77-87).
-// Pass 1 writes only hole pixels and reads only valid ones, so it is race-free in place.
-// Pass 2 is expressed as a row indirection src[] instead of copying rows.
-__device__ __forceinline__ void interpolate_and_fill(const TailSmem& S, int rows, bool enabled) {
+// One warp per row: (optionally) turn the scattered keys into ranges, build the validity mask
+// (valid <=> value > 0, range_image.py:35) and fill the holes of the row by circular linear
+// interpolation (range_image.py:33-64). Everything a row needs was produced by the same warp,
+// so no block barrier separates the three steps. FROM_KEYS: the row holds the bits of the min
+// of s per pixel (plus the 361st column for azimuth == 2 pi); `to_value(key)` maps them to ranges.
+// `stage0`, if not null, receives the un-interpolated rows (rows x 360, global memory).
+template <bool FROM_KEYS, typename ToValue>
+__device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool interpolate,
+                                               float* __restrict__ stage0, ToValue to_value) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (enabled) {
-        for (int r = warp; r < rows; r += kWarps) {
-            const int nv = S.nvalid[r];
-            if (nv == 0 || nv == kAz) continue;
-            const uint32_t* m = S.mask + r * kMaskWords;
-            float* row = S.img + r * kPitch;
+    for (int r = warp; r < rows; r += kWarps) {
+        float* row = S.img + r * kPitch;
+        uint32_t* m = S.mask + r * kMaskWords;
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kMaskWords; ++w) {
+            const int c = w * 32 + lane;
+            float v = 0.0f;
+            if (c < kAz) {
+                if (FROM_KEYS) {
+                    uint32_t key = __float_as_uint(row[c]);
+                    if (c == 0) key = min(key, __float_as_uint(row[kAz]));   // azimuth == 2 pi -> column 0
+                    v = to_value(key);
+                    row[c] = v;
+                } else {
+                    v = row[c];
+                }
+                if (stage0) stage0[r * kAz + c] = v;
+            }
+            const uint32_t bits = __ballot_sync(0xffffffffu, v > 0.0f);
+            cnt += __popc(bits);
+            if (lane == 0) m[w] = bits;
+        }
+        if (lane == 0) S.nvalid[r] = cnt;
+        __syncwarp();
+        if (interpolate && cnt != 0 && cnt != kAz) {
+            // writes only hole pixels and reads only valid ones: race-free in place
             for (int x = lane; x < kAz; x += 32) {
                 if ((m[x >> 5] >> (x & 31)) & 1u) continue;
                 const int xl = prev_valid(m, x), xr = next_valid(m, x);
@@ -148,12 +158,13 @@ __device__ __forceinline__ void interpolate_and_fill(const TailSmem& S, int rows
         }
     }
     __syncthreads();
-    // Rows with no pixel > 0 copy the nearest filled row below, leading ones the first non-empty
-    // row above; an all-empty image stays zero (sequential in-place semantics of :77-87).
+    // Empty-row fill (range_image.py:77-87) as a row indirection src[] instead of copies: rows with
+    // no pixel > 0 take the nearest filled row below, leading ones the first non-empty row above;
+    // an all-empty image stays zero (the sequential in-place semantics of the reference).
     if (threadIdx.x < rows) {
         const int r = threadIdx.x;
         int s = r;
-        if (enabled && S.nvalid[r] == 0) {
+        if (interpolate && S.nvalid[r] == 0) {
             int k = r - 1;
             while (k >= 0 && S.nvalid[k] == 0) --k;
             if (k < 0) {
@@ -189,12 +200,15 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ x, float2* _
     }
 }
 
-// Rows [2*g0, 2*(g0+n)) of the (pooled) image -> complex signals -> spectra -> bin sums.
+// Rows of the (pooled) image, two per complex signal -> spectra -> magnitudes -> bin sums in
+// S.hist (un-normalised). The mapping hist index -> thread (i = tid + k * kThreads) is the one
+// normalise_and_store() uses, so no barrier is needed between the two for S.hist.
 template <typename P>
 __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp, int rows) {
     const int T = dp.T, nb = dp.n_bins;
     const int n_sig_total = (T + 1) / 2;
     const int cap = n_sig_total < kMaxSignals ? n_sig_total : kMaxSignals;
+    float* mag = reinterpret_cast<float*>(S.fa);           // 2 * n_sig x 181, valid after the last pass
     for (int g0 = 0; g0 < n_sig_total; g0 += cap) {
         const int n_sig = min(cap, n_sig_total - g0);
         for (int t = threadIdx.x; t < n_sig * kAz; t += kThreads) {
@@ -211,24 +225,29 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
         __syncthreads();
         fft_pass<5, 72>(S.fa, S.fb, S.tw, n_sig);
         __syncthreads();
-        // Z = FFT(a + i b): A[k] = (Z[k] + conj Z[-k]) / 2, B[k] = (Z[k] - conj Z[-k]) / 2i.
-        for (int t = threadIdx.x; t < n_sig * nb; t += kThreads) {
-            const int g = t / nb, b = t - g * nb;
+        // Z = FFT(a + i b): A[k] = (Z[k] + conj Z[-k]) / 2, B[k] = (Z[k] - conj Z[-k]) / 2i; one
+        // thread per (signal, frequency), both magnitudes (fa is free again: the spectrum is in fb)
+        for (int t = threadIdx.x; t < n_sig * kFreqs; t += kThreads) {
+            const int g = t / kFreqs, k = t - g * kFreqs;
             const float2* z = S.fb + g * kAz;
-            float ha = 0.0f, hb = 0.0f;
-            const int k1 = dp.bin_start[b + 1];
-            for (int k = dp.bin_start[b]; k < k1; ++k) {   // ascending k: scatter_add_ order
-                const float2 p = z[k], m = z[k == 0 ? 0 : kAz - k];
-                const float ar = p.x + m.x, ai = p.y - m.y;
-                const float br = p.y + m.y, bi = p.x - m.x;
-                ha += 0.5f * __fsqrt_rn(fmaf(ar, ar, ai * ai));
-                hb += 0.5f * __fsqrt_rn(fmaf(br, br, bi * bi));
-            }
-            const int ra = 2 * (g0 + g);
-            S.hist[ra * nb + b] = ha;
-            if (ra + 1 < T) S.hist[(ra + 1) * nb + b] = hb;
+            const float2 p = z[k], m = z[k == 0 ? 0 : kAz - k];
+            const float ar = p.x + m.x, ai = p.y - m.y;
+            const float br = p.y + m.y, bi = p.x - m.x;
+            mag[(2 * g) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(ar, ar, ai * ai));
+            mag[(2 * g + 1) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(br, br, bi * bi));
         }
         __syncthreads();
+        // contiguous-frequency bin sums in ascending k: the CPU order of scatter_add_
+        const int row0 = 2 * g0, row1 = min(T, 2 * (g0 + n_sig));
+        for (int i = threadIdx.x; i < T * nb; i += kThreads) {
+            const int r = i / nb, b = i - r * nb;
+            if (r < row0 || r >= row1) continue;
+            const float* mr = mag + (r - row0) * kFreqs;
+            float h = 0.0f;
+            for (int k = dp.bin_start[b], k1 = dp.bin_start[b + 1]; k < k1; ++k) h += mr[k];
+            S.hist[i] = h;
+        }
+        if (g0 + cap < n_sig_total) __syncthreads();   // the next batch overwrites fa / fb
     }
 }
 
@@ -245,7 +264,7 @@ __device__ __forceinline__ void normalise_and_store(const TailSmem& S, const P& 
     const int D = dp.T * dp.n_bins;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < D; i += kThreads) acc += (double)S.hist[i];
+    for (int i = threadIdx.x; i < D; i += kThreads) acc += (double)S.hist[i];   // own entries only
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if (lane == 0) S.red[warp] = acc;
@@ -261,7 +280,7 @@ __device__ __forceinline__ void normalise_and_store(const TailSmem& S, const P& 
         if (out) out[i] = v;
         for (int p = 0; p < peers.n; ++p) peers.ptr[p][peer_row * D + i] = v;
     }
-    __syncthreads();   // hist / red are reused by the next scan
+    // S.red / S.hist are next written after the barriers at the top of the next scan
 }
 
 }  // namespace nsc
