@@ -481,3 +481,26 @@ def test_other_encoder_geometries_against_the_oracle(kw):
         got = enc.encode_points(st).cpu().numpy()                               # cluster kernel
         assert_descriptor(got, orc.encode_points(st, cfg).numpy())
         assert np.abs(d[i] - orc.encode_points(scans[i], cfg).numpy()).max() < 2e-4
+
+
+def test_full_size_invariances():
+    """Size-independent properties at BASELINE size (120 k points): the descriptor depends only on
+    the per-pixel minimum, so duplicating the cloud, permuting it, or adding points that the
+    filters drop (NaN, beyond 80 m, closer than 1 m) or that lie behind closer returns leaves every
+    bit unchanged."""
+    from neural_spectral_codec_b200 import synth
+    enc = make_encoder()
+    p = synth.make_scan(synth.HDL64, 77, device="cuda")
+    base = enc.encode_points(p)
+    n = p.shape[0]
+    g = torch.Generator(device="cuda").manual_seed(1)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    assert torch.equal(enc.encode_points(p[perm]), base)
+    assert torch.equal(enc.encode_points(torch.cat([p, p[perm[: n // 2]]])), base)
+    junk = torch.cat([p[:1000] * 100.0, p[1000:2000] * 1e-3, torch.full((500, 4), float("nan"), device="cuda"),
+                      torch.full((10, 4), float("inf"), device="cuda")])
+    assert torch.equal(enc.encode_points(torch.cat([junk, p, junk])), base)
+    behind = p[: n // 3].clone()
+    behind[:, :3] *= 1.0 + 0.2 * torch.rand(behind.shape[0], 1, device="cuda", generator=g)   # same ray, farther
+    keep = (behind[:, :3].norm(dim=1) < 79.0)
+    assert torch.equal(enc.encode_points(torch.cat([p, behind[keep]])), base)
