@@ -313,6 +313,17 @@ int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, con
     e = cudaSetDevice(pl->device);
     if (e != cudaSuccess) return record_cuda(e);
 
+    // pinned staging for every slot, allocated on the first call of this entry point
+    for (int i = 0; i < pl->n_buffers; ++i) {
+        nsc_pipeline::Slot& s = pl->slot[i];
+        if (s.h_stage) continue;
+        if ((e = cudaHostAlloc(&s.h_stage, (size_t)pl->max_chunk_points * 16, cudaHostAllocDefault)) != cudaSuccess ||
+            (e = cudaHostAlloc(&s.h_offsets, (size_t)(kMaxChunkScans + 1) * 8, cudaHostAllocDefault)) != cudaSuccess ||
+            (e = cudaHostAlloc(&s.h_out, (size_t)kMaxChunkScans * kMaxDescriptor * 4, cudaHostAllocDefault)) != cudaSuccess) {
+            cudaSetDevice(prev);
+            return record_cuda(e);
+        }
+    }
     struct Pending { int first, count; };
     Pending pending[4] = {};
     auto retire = [&](int k) -> int {      // wait for slot k and hand its descriptors to the caller
@@ -333,14 +344,6 @@ int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, con
         const int slot_i = k % pl->n_buffers;
         nsc_pipeline::Slot& s = pl->slot[slot_i];
         if ((st = retire(slot_i)) != NSC_OK) break;
-        if (!s.h_stage) {
-            if ((e = cudaHostAlloc(&s.h_stage, (size_t)pl->max_chunk_points * 16, cudaHostAllocDefault)) != cudaSuccess ||
-                (e = cudaHostAlloc(&s.h_offsets, (size_t)(kMaxChunkScans + 1) * 8, cudaHostAllocDefault)) != cudaSuccess ||
-                (e = cudaHostAlloc(&s.h_out, (size_t)kMaxChunkScans * kMaxDescriptor * 4, cudaHostAllocDefault)) != cudaSuccess) {
-                st = record_cuda(e);
-                break;
-            }
-        }
         const int ns = last - first;
         stage_scans(s.h_stage, h_scans, h_counts, first, last, point_stride, s.h_offsets);
         if ((e = cudaMemcpyAsync(s.d_points, s.h_stage, (size_t)np * point_stride * 4,
