@@ -184,6 +184,24 @@ def test_row_rules_on_other_fields_of_view(lib, er, rows, mode):
     np.testing.assert_array_equal(col[clear], ocol[clear])
 
 
+@pytest.mark.parametrize("lo,hi", [(0.5, 120.0), (2.0, 50.0), (0.0, 30.0), (1.0, 80.0)])
+def test_keep_drop_is_exact_for_other_range_limits(lib, lo, hi):
+    """The float32 thresholds on s are derived per (min_range, max_range); the keep/drop decision
+    must equal the oracle's test on sqrt(s) for ranges packed around both limits."""
+    rng = np.random.default_rng(int(hi))
+    n = 60000
+    r = np.concatenate([lo + rng.normal(0, 2e-6, n // 3) * max(lo, 1.0), hi + rng.normal(0, 2e-6, n // 3) * hi,
+                        rng.uniform(0.01, hi * 1.5, n - 2 * (n // 3))])
+    az, el = rng.uniform(-np.pi, np.pi, n), rng.uniform(-0.4, 0.02, n)
+    pts = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)], 1).astype(np.float32)
+    cfg = orc.OracleConfig(min_range=lo, max_range=hi)
+    _, _, keep = host_classify(lib, pts, min_range=lo, max_range=hi)
+    okeep = np.zeros(n, bool)
+    okeep[orc.spherical(pts, cfg)["kept"]] = True
+    np.testing.assert_array_equal(keep, okeep)
+    assert 0.1 * n < keep.sum() < 0.95 * n
+
+
 def test_range_thresholds_are_exact_preimages(lib):
     """the filter on s = x^2+y^2+z^2 must keep exactly the points whose
     float32 sqrt lies in [min_range, max_range], including the last ulps around 1 and 80."""
