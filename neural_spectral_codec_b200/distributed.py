@@ -92,6 +92,9 @@ class ShardedEncoder:
             lib = _lib.load()
             from .encoder import _check_batch
             points, offsets, n, stride = _check_batch(points, offsets)
+            # Peers store into this rank's database from THEIR streams: nobody may start writing
+            # pass k+1 before every rank's stream is past its reads of pass k.
+            self._hdl.barrier()
             p = self.encoder._params()
             lut = self.encoder.freq_to_bin()
             with torch.cuda.device(self.device):
