@@ -303,8 +303,25 @@ __device__ __forceinline__ void point_pass(const float* __restrict__ points, lon
 
 // Everything after the scatter for one scan: keys -> ranges, interpolation, (optional) image
 // output, spectrum, bins, normalisation, descriptor store. CTA-collective.
+#ifdef NSC_PHASE_TIMING
+// Tuning build: thread 0 of every CTA accumulates the cycles it spends in each phase of a scan
+// into counter[4 + 2*phase] (64-bit), phases: 0 init, 1 point pass, 2 rows_to_filled,
+// 3 spectrum_and_bins, 4 normalise. Read back by tools/phase_timing.py.
+#define NSC_PHASE(p)                                                                         \
+    do {                                                                                     \
+        if (threadIdx.x == 0) {                                                              \
+            const long long now_ = clock64();                                                \
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.counter) + 2 + (p),            \
+                      (unsigned long long)(now_ - phase_t0));                                \
+            phase_t0 = now_;                                                                 \
+        }                                                                                    \
+    } while (0)
+#else
+#define NSC_PHASE(p) do { } while (0)
+#endif
+
 __device__ __forceinline__ void finish_scan(const EncodeArgs& a, const DeviceParams& dp,
-                                            const TailSmem& S, int scan) {
+                                            const TailSmem& S, int scan, long long& phase_t0) {
     const int tid = threadIdx.x;
     const int D = dp.T * dp.n_bins;
     // bits of min s -> range = sqrt_rn(s); empty -> 0 (range_image.py:162,:214); masks; hole
@@ -320,11 +337,19 @@ __device__ __forceinline__ void finish_scan(const EncodeArgs& a, const DevicePar
             a.img_out[(long long)scan * dp.E * kAz + i] = S.img[S.src[r] * kPitch + c];
         }
     }
+    NSC_PHASE(2);
     if (a.out || a.peers.n > 0) {
+#ifdef NSC_PHASE_TIMING
+        spectrum_and_bins(S, dp, dp.E, [&](int p) { NSC_PHASE(p); });
+#else
         spectrum_and_bins(S, dp, dp.E);
+#endif
+        NSC_PHASE(3);
         normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
                             a.peers.row0 + scan);
+        NSC_PHASE(4);
     }
+    (void)phase_t0;
 }
 
 template <int STRIDE, int ROWMODE, int FEED>
@@ -339,13 +364,20 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
     const int tid = threadIdx.x;
     const int n_pix = dp.E * kPitch;
 
-    init_twiddles(S.tw);
+    init_tail_tables(S, dp);
     uint32_t g_stage = 0;
     if (FEED == kFeedTma) tma_ring_init(smem_raw + L.ring_off);
+    long long phase_t0 = clock64();
+    // Thread 0 always holds the NEXT scan index: the atomic's round trip (~1 us) is issued at the
+    // top of a scan and only consumed at the top of the following one.
+    int next_scan = tid == 0 ? (int)atomicAdd(a.counter, 1u) : 0;
 
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_scan = (int)atomicAdd(a.counter, 1u);
+        if (tid == 0) {
+            s_scan = next_scan;
+            if (next_scan < a.n_scans) next_scan = (int)atomicAdd(a.counter, 1u);
+        }
         for (int i = tid; i < n_pix; i += kThreads) img[i] = kInfBits;
         // The ring doubles as FFT scratch in the tail: every thread orders its generic-proxy
         // writes before the barrier, the bulk copies (async proxy) are issued after it.
@@ -355,9 +387,11 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
         if (scan >= a.n_scans) break;
         const long long beg = a.offsets[scan] - a.origin;
         const int n = (int)(a.offsets[scan + 1] - a.offsets[scan]);
+        NSC_PHASE(0);
         point_pass<STRIDE, ROWMODE, FEED>(a.points, beg, n, dp, img_biased, smem_raw + L.ring_off, g_stage);
         __syncthreads();
-        finish_scan(a, dp, S, scan);
+        NSC_PHASE(1);
+        finish_scan(a, dp, S, scan, phase_t0);
     }
 }
 
@@ -381,7 +415,7 @@ encode_points_split_kernel(const __grid_constant__ EncodeArgs a, const __grid_co
     const int n_pix = dp.E * kPitch;
     const int scan = blockIdx.x / csize;      // grid = n_scans * cluster size
 
-    if (rank == 0) init_twiddles(S.tw);
+    if (rank == 0) init_tail_tables(S, dp);
     uint32_t g_stage = 0;
     if (FEED == kFeedTma) tma_ring_init(smem_raw + L.ring_off);
     for (int i = tid; i < n_pix; i += kThreads) img[i] = kInfBits;
@@ -402,7 +436,8 @@ encode_points_split_kernel(const __grid_constant__ EncodeArgs a, const __grid_co
     cluster.sync();                           // peers may exit only after the leader has read them
     if (rank == 0) {
         __syncthreads();
-        finish_scan(a, dp, S, scan);
+        long long phase_t0 = 0;
+        finish_scan(a, dp, S, scan, phase_t0);
     }
 }
 
@@ -415,7 +450,7 @@ encode_images_kernel(const float* __restrict__ images, int n_images, int rows,
     const SmemLayout L(rows, dp.T, dp.n_bins);
     const TailSmem S(smem_raw, L);
     const int D = dp.T * dp.n_bins;
-    init_twiddles(S.tw);
+    init_tail_tables(S, dp);
     if (threadIdx.x < rows) S.src[threadIdx.x] = threadIdx.x;
     PeerOut none;
     none.n = 0;
@@ -617,7 +652,11 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     int per_sm = 0;
     st = configure(kernel, L.total, di, &per_sm);
     if (st != NSC_OK) return st;
+#ifdef NSC_PHASE_TIMING
+    cudaError_t e = cudaMemsetAsync(d_workspace, 0, 128, stream);
+#else
     cudaError_t e = cudaMemsetAsync(d_workspace, 0, 2 * sizeof(unsigned), stream);
+#endif
     if (e != cudaSuccess) return record_cuda(e);
     int grid = di.sms * per_sm;
     if (grid > n_scans) grid = n_scans;

@@ -35,7 +35,7 @@ constexpr int kCpRingBytes = kCpDepth * kCpPts * kThreads * 16;   // 65 536 B pe
 // FFT buffers alias it: the ring is idle (fully consumed) while the tail runs.
 struct SmemLayout {
     int img_off, tw_off, fa_off, fb_off, hist_off, mask_off, nvalid_off, src_off, red_off;
-    int ring_off, total;
+    int ring_off, bins_off, total;
     int n_sig;  // complex FFTs per batch
     __host__ __device__ SmemLayout(int rows, int T, int n_bins, int ring_bytes = 0) {
         const bool ring = ring_bytes > 0;
@@ -57,6 +57,7 @@ struct SmemLayout {
         nvalid_off = take(rows * 4);
         src_off = take(rows * 4);
         red_off = take(kWarps * 8 + 16);
+        bins_off = take(NSC_MAX_BINS + 3);
         total = o;
     }
 };
@@ -71,20 +72,24 @@ struct TailSmem {
     int* nvalid;
     int* src;          // row r of the filled image is stored row src[r]
     double* red;
+    uint8_t* bin_start;  // copy of DeviceParams::bin_start: per-thread indices would serialise in the constant bank
     __device__ TailSmem(unsigned char* base, const SmemLayout& L)
         : img((float*)(base + L.img_off)), tw((float2*)(base + L.tw_off)),
           fa((float2*)(base + L.fa_off)), fb((float2*)(base + L.fb_off)),
           hist((float*)(base + L.hist_off)), mask((uint32_t*)(base + L.mask_off)),
           nvalid((int*)(base + L.nvalid_off)), src((int*)(base + L.src_off)),
-          red((double*)(base + L.red_off)) {}
+          red((double*)(base + L.red_off)), bin_start(base + L.bins_off) {}
 };
 
-__device__ __forceinline__ void init_twiddles(float2* tw) {
+// Per-CTA constants of the tail: FFT twiddles and the bin boundaries.
+template <typename P>
+__device__ __forceinline__ void init_tail_tables(const TailSmem& S, const P& dp) {
     for (int m = threadIdx.x; m < kAz; m += kThreads) {
         float s, c;
         sincospif((float)m * (1.0f / 180.0f), &s, &c);   // angle = 2 pi m / 360
-        tw[m] = make_float2(c, -s);
+        S.tw[m] = make_float2(c, -s);
     }
+    for (int b = threadIdx.x; b <= dp.n_bins; b += kThreads) S.bin_start[b] = dp.bin_start[b];
 }
 
 // Nearest valid column strictly left / right of x on the circular row; the returned position
@@ -203,8 +208,14 @@ __device__ __forceinline__ void fft_pass(const float2* __restrict__ x, float2* _
 // Rows of the (pooled) image, two per complex signal -> spectra -> magnitudes -> bin sums in
 // S.hist (un-normalised). The mapping hist index -> thread (i = tid + k * kThreads) is the one
 // normalise_and_store() uses, so no barrier is needed between the two for S.hist.
-template <typename P>
-__device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp, int rows) {
+struct NoMark {
+    __device__ __forceinline__ void operator()(int) const {}
+};
+// `mark(p)` is a tuning hook called by thread-uniform code between the sub-phases (5 = signals
+// loaded, 6..8 = after each FFT pass, 9 = magnitudes); a no-op in product builds.
+template <typename P, typename Mark = NoMark>
+__device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp, int rows,
+                                                  Mark mark = Mark()) {
     const int T = dp.T, nb = dp.n_bins;
     const int n_sig_total = (T + 1) / 2;
     const int cap = n_sig_total < kMaxSignals ? n_sig_total : kMaxSignals;
@@ -219,12 +230,16 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
             S.fa[t] = make_float2(a, b);
         }
         __syncthreads();
+        mark(5);
         fft_pass<8, 1>(S.fa, S.fb, S.tw, n_sig);
         __syncthreads();
+        mark(6);
         fft_pass<9, 8>(S.fb, S.fa, S.tw, n_sig);
         __syncthreads();
+        mark(7);
         fft_pass<5, 72>(S.fa, S.fb, S.tw, n_sig);
         __syncthreads();
+        mark(8);
         // Z = FFT(a + i b): A[k] = (Z[k] + conj Z[-k]) / 2, B[k] = (Z[k] - conj Z[-k]) / 2i; one
         // thread per (signal, frequency), both magnitudes (fa is free again: the spectrum is in fb)
         for (int t = threadIdx.x; t < n_sig * kFreqs; t += kThreads) {
@@ -237,6 +252,7 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
             mag[(2 * g + 1) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(br, br, bi * bi));
         }
         __syncthreads();
+        mark(9);
         // contiguous-frequency bin sums in ascending k: the CPU order of scatter_add_
         const int row0 = 2 * g0, row1 = min(T, 2 * (g0 + n_sig));
         for (int i = threadIdx.x; i < T * nb; i += kThreads) {
@@ -244,7 +260,7 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
             if (r < row0 || r >= row1) continue;
             const float* mr = mag + (r - row0) * kFreqs;
             float h = 0.0f;
-            for (int k = dp.bin_start[b], k1 = dp.bin_start[b + 1]; k < k1; ++k) h += mr[k];
+            for (int k = S.bin_start[b], k1 = S.bin_start[b + 1]; k < k1; ++k) h += mr[k];
             S.hist[i] = h;
         }
         if (g0 + cap < n_sig_total) __syncthreads();   // the next batch overwrites fa / fb
