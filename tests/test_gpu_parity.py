@@ -504,3 +504,27 @@ def test_full_size_invariances():
     behind[:, :3] *= 1.0 + 0.2 * torch.rand(behind.shape[0], 1, device="cuda", generator=g)   # same ray, farther
     keep = (behind[:, :3].norm(dim=1) < 79.0)
     assert torch.equal(enc.encode_points(torch.cat([p, behind[keep]])), base)
+
+
+def test_reference_vectors_for_other_constructor_arguments():
+    """The CUDA path against the reference's recorded outputs for non-default alpha, n_bins, epsilon,
+    elevation_range (incl. the +-60 degree field of view that switches to threshold rows) and row counts."""
+    from test_oracle_golden import ctor_cases, oracle_config
+    g, cases = ctor_cases()
+    for i, case in enumerate(cases):
+        kw = {k: (tuple(v) if k == "elevation_range" else v) for k, v in case.items() if k != "points"}
+        enc = make_encoder(**kw)
+        cfg = oracle_config(case)
+        pts = np.load(os.path.join(GOLDEN_DIR, case["points"] + ".npz"))["points"]
+        np.testing.assert_array_equal(enc.freq_to_bin(), g[f"freq_to_bin{i}"])
+        img, _ = enc.projector.project(pts, keep_intensity=False)
+        diff = int((img != g[f"range_image{i}"]).sum())
+        assert diff <= n_ambiguous(pts, cfg), (i, diff)
+        d = enc.encode_points(pts).cpu().numpy()
+        assert d.shape == g[f"descriptor{i}"].shape
+        if diff == 0:
+            assert_descriptor(d, g[f"descriptor{i}"])
+        else:
+            assert np.abs(d - g[f"descriptor{i}"]).max() < 1e-4
+        st = orc.strip_ambiguous(pts, cfg)
+        assert_descriptor(enc.encode_points(st).cpu().numpy(), orc.encode_points(st, cfg).numpy())

@@ -116,3 +116,33 @@ def test_oracle_intensity_image_matches_reference_vectors():
         else:
             assert (r != g[name + "_range"]).sum() <= 16
     assert orc.project_with_intensity(g["nonfinite_points"][:, :3], cfg)[1] is None
+
+
+def ctor_cases():
+    import json
+    g = np.load(os.path.join(GOLDEN_DIR, "ctor_params.npz"))
+    return g, json.loads(str(g["cases"]))
+
+
+def oracle_config(case):
+    kw = {k: v for k, v in case.items() if k not in ("points", "learnable_alpha")}
+    if "elevation_range" in kw:
+        kw["elevation_range"] = tuple(kw["elevation_range"])
+    return orc.OracleConfig(**kw)
+
+
+def test_oracle_matches_reference_for_other_constructor_arguments():
+    """alpha, n_bins, epsilon, elevation_range, n_elevation / target rows other than the shipped
+    config, recorded from the unmodified reference (tests/golden/make_golden_params.py)."""
+    g, cases = ctor_cases()
+    for i, case in enumerate(cases):
+        cfg = oracle_config(case)
+        pts = np.load(os.path.join(GOLDEN_DIR, case["points"] + ".npz"))["points"]
+        st = orc.stages(pts, cfg)
+        np.testing.assert_array_equal(st["freq_to_bin"], g[f"freq_to_bin{i}"])
+        if same_platform():
+            np.testing.assert_array_equal(st["range_image"], g[f"range_image{i}"])
+            np.testing.assert_array_equal(st["interpolated"], g[f"interpolated{i}"])
+            np.testing.assert_array_equal(st["descriptor"], g[f"descriptor{i}"])
+        else:
+            assert (st["range_image"] != g[f"range_image{i}"]).sum() <= 16
