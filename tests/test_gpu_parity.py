@@ -116,6 +116,8 @@ def test_interpolate_entry_matches_reference_vectors():
         if name == "no_interp":
             continue
         np.testing.assert_array_equal(interpolate_range_image(g["range_image"]), g["interpolated"])
+    g = np.load(os.path.join(GOLDEN_DIR, "interp_random.npz"))      # recorded from the reference
+    np.testing.assert_array_equal(interpolate_range_image(g["images"]), g["interpolated"])
     rng = np.random.default_rng(5)
     imgs = (rng.uniform(1, 60, (40, 16, 360)) * (rng.uniform(0, 1, (40, 16, 360)) > 0.7)).astype(np.float32)
     imgs[3, 4:9] = 0

@@ -146,3 +146,9 @@ def test_oracle_matches_reference_for_other_constructor_arguments():
             np.testing.assert_array_equal(st["descriptor"], g[f"descriptor{i}"])
         else:
             assert (st["range_image"] != g[f"range_image{i}"]).sum() <= 16
+
+
+def test_oracle_interpolation_matches_reference_on_random_sparse_images():
+    g = np.load(os.path.join(GOLDEN_DIR, "interp_random.npz"))
+    for img, want in zip(g["images"], g["interpolated"]):
+        np.testing.assert_array_equal(orc.interpolate_range_image(img), want)
