@@ -530,3 +530,9 @@ def test_reference_vectors_for_other_constructor_arguments():
             assert np.abs(d - g[f"descriptor{i}"]).max() < 1e-4
         st = orc.strip_ambiguous(pts, cfg)
         assert_descriptor(enc.encode_points(st).cpu().numpy(), orc.encode_points(st, cfg).numpy())
+
+
+def test_graft_entry_smoke_passes():
+    """The driver's smoke() entry point, so that the suite catches a regression of it."""
+    import __graft_entry__
+    __graft_entry__.smoke()
