@@ -310,7 +310,7 @@ def run_gpu_arm(args):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        per_core = 24
+        per_core = 64
         v, n = cpu_oracle_throughput(per_core, cores)
         # the reference's native call pattern: one process looping encode_points (pipeline.py:336-354)
         from oracle import nsc_oracle as orc
