@@ -78,7 +78,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = 4
+    per_core = 16
     steps = max(1, min(args.steps, 5))
     warmup = min(args.warmup, 1)
     vals, ms = [], []
