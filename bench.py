@@ -8,14 +8,23 @@ A step = one pass of the fused encode kernel over this rank's batch of synthetic
 HBM before timing), followed for N > 1 by the gather of the 800-D descriptors into the database
 replicated on every GPU. Weak scaling: every rank holds its own 4541 scans.
 
-Prints ONE JSON line (rank 0). ``value`` is device-timed whole-job throughput; ``e2e`` is the
-same metric through ``SpectralEncoder.encode_scans`` with pinned HOST buffers (H2D + kernel +
-D2H inside the timed region); ``roofline`` is the fused kernel against the measured HBM peak;
-``cpu_baseline`` is the CPU oracle (a port of the reference encoder) on the host cores.
+Prints ONE JSON line (rank 0):
+  value         device-timed whole-job throughput (CUDA events, max over ranks)
+  roofline      the fused kernel against the measured HBM peak (events around each launch)
+  e2e           the same metric through ``SpectralEncoder.encode_scans`` with pinned HOST buffers
+                (H2D + kernel + D2H inside the timed region), with the bare pinned-H2D rate of
+                the same bytes beside it (``h2d_ceiling_gbs_per_gpu``), the reference's own call
+                pattern (``per_scan``: one ``encode_points(numpy)`` per scan) and pageable lists
+  checks        made AFTER the timed region on the timed output: rows of ``out`` against the CPU
+                oracle, and for N > 1 the gathered database against an NCCL all-gather of the
+                single-GPU encodes, on every rank. A failed check exits non-zero.
+  configs       the other BASELINE.json shapes (HDL-32, 128-beam, shuffled order) at reduced step
+                counts, each with its own roofline fraction and CPU baseline   (N = 1)
+  c5            BASELINE.json configs[4]: 100 000 scans sharded over the ranks        (N > 1)
+  cpu_baseline  the reference's CPU encoder on all host cores (``kind: "reference"`` when the
+                git-ignored copy made by oracle/make_ref.py is present, else the oracle port)
 
-``--impl reference`` times the reference's CPU algorithm (the oracle port: the reference is
-Python and /root/reference does not exist on the GPU box) with all host cores on the same
-workload, a bounded sample per step.
+``--impl reference`` times that same CPU encoder as the reference arm, honouring --steps/--warmup.
 """
 import argparse
 import json
@@ -34,10 +43,11 @@ METRIC = "scans_per_sec_encoded_to_800d"
 UNIT = "scans/s"
 N_SCANS = 4541            # KITTI sequence 00 length (BASELINE.json configs[1])
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
-
+ENCODER_DESC = "n_elevation=16 n_azimuth=360 n_bins=50 alpha=2.0 target_rows=16"
 
 SHAPE_DESC = {"hdl64": "HDL-64-shaped scans x ~120k xyzi points", "hdl32": "NCLT HDL-32-shaped scans x ~70k xyzi points",
               "beam128": "128-beam dense scans x ~260k xyzi points"}
+SHAPE_GB = {"hdl64": 1.93e-3, "hdl32": 1.13e-3, "beam128": 4.15e-3}   # GB per scan, for the config text
 
 
 def workload_name(n, shape="hdl64", shuffle=False):
@@ -45,61 +55,101 @@ def workload_name(n, shape="hdl64", shuffle=False):
     return f"{head}: {n} {SHAPE_DESC[shape]} per GPU" + (" (shuffled point order)" if shuffle else "")
 
 
+def make_config(args, world):
+    """The ``config`` object; identical for the GPU arm and the reference arm of one invocation."""
+    return {"workload": workload_name(args.scans, args.shape, args.shuffle), "scans_per_gpu": args.scans,
+            "l2": f"inputs (~{args.scans * SHAPE_GB[args.shape]:.1f} GB per GPU) larger than the 126 MB L2, no flush needed",
+            "gather": ("none (single GPU)" if world == 1 else args.gather), "encoder": ENCODER_DESC}
+
+
 # ----------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
-    """Encode ``count`` scans starting at ``first`` with the oracle; returns (count, seconds)."""
-    first, count = args
+def reference_src():
+    """sys.path entry of the unmodified reference (oracle/make_ref.py), or None."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    try:
+        import make_ref
+        return make_ref.ref_src_path()
+    except Exception:
+        return None
+    finally:
+        sys.path.pop(0)
+
+
+def make_cpu_encoder(kind):
+    """``encode(points np (N,4)) -> descriptor`` of the reference's CPU path.
+    kind "reference": the reference's own SpectralEncoder, constructed as its callers do
+    (train_multi_dataset.py:264-271); kind "port": oracle/nsc_oracle.py."""
+    if kind == "reference":
+        src = reference_src()
+        if src not in sys.path:
+            sys.path.insert(0, src)
+        from encoding.spectral_encoder import SpectralEncoder as RefEncoder
+        enc = RefEncoder(n_elevation=16, n_azimuth=360, n_bins=50, alpha=2.0, learnable_alpha=True,
+                         target_elevation_bins=16)
+        return lambda pts: enc.encode_points(pts).detach().cpu().numpy()
+    from oracle import nsc_oracle as orc
+    cfg = orc.OracleConfig()
+    return lambda pts: orc.encode_points(pts, cfg).numpy()
+
+
+def _cpu_worker(job):
+    """Encode ``count`` scans starting at seed ``first``; returns (count, seconds)."""
+    first, count, shape, shuffle, kind = job
     import torch
     torch.set_num_threads(1)
     from neural_spectral_codec_b200 import synth
-    from oracle import nsc_oracle as orc
-    cfg = orc.OracleConfig()
-    scans = [synth.make_scan(synth.HDL64, first + i).numpy() for i in range(count)]
+    encode = make_cpu_encoder(kind)
+    scans = [synth.make_scan(synth.SHAPES[shape], first + i, shuffle=shuffle).numpy() for i in range(count)]
     t0 = time.perf_counter()
     for s in scans:
-        orc.encode_points(s, cfg)
+        encode(s)
     return count, time.perf_counter() - t0
 
 
-def cpu_oracle_throughput(scans_per_core: int, cores: int, pool=None):
-    """All-cores throughput of the oracle: each worker generates its own scans from seeds (not
-    timed) and encodes them single-threaded; throughput = sum over workers of count / time."""
-    jobs = [(100000 + w * scans_per_core, scans_per_core) for w in range(cores)]
-    if pool is not None:
-        res = pool.map(_cpu_worker, jobs, chunksize=1)
-    else:
-        with mp.get_context("spawn").Pool(cores) as p:
-            res = p.map(_cpu_worker, jobs, chunksize=1)
+def cpu_throughput(pool, scans_per_core, cores, kind, shape="hdl64", shuffle=False, first=100000):
+    """All-cores throughput: each worker generates its own scans from seeds (not timed) and encodes
+    them single-threaded; throughput = sum over workers of count / time."""
+    jobs = [(first + w * scans_per_core, scans_per_core, shape, shuffle, kind) for w in range(cores)]
+    res = pool.map(_cpu_worker, jobs, chunksize=1)
     return sum(c / t for c, t in res), sum(c for c, _ in res)
+
+
+def cpu_kind():
+    return "reference" if reference_src() else "port"
+
+
+def cpu_kind_text(kind):
+    return ("the reference's own SpectralEncoder.encode_points (verbatim copy of its Python files, oracle/make_ref.py)"
+            if kind == "reference" else "oracle/nsc_oracle.py (port of the reference's Python encoder)")
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
-    per_core = 16
-    steps = max(1, min(args.steps, 5))
-    warmup = min(args.warmup, 1)
+    kind = cpu_kind()
+    # bounded sample per step: the whole --steps/--warmup run stays within ~2 minutes
+    per_core = int(max(2, min(16, 120.0 / max(1, args.steps + args.warmup) / 0.03)))
     vals, ms = [], []
     with mp.get_context("spawn").Pool(cores) as pool:
-        for _ in range(warmup):
-            cpu_oracle_throughput(1, cores, pool)
-        for _ in range(steps):
+        for _ in range(args.warmup):
+            cpu_throughput(pool, per_core, cores, kind, args.shape, args.shuffle)
+        for _ in range(args.steps):
             t0 = time.perf_counter()
-            v, n = cpu_oracle_throughput(per_core, cores, pool)
+            v, _n = cpu_throughput(pool, per_core, cores, kind, args.shape, args.shuffle)
             ms.append(1e3 * (time.perf_counter() - t0))
             vals.append(v)
     value = statistics.median(vals)
-    sample = (f"{per_core} scans per core x {cores} cores per step, {steps} steps (of {args.steps} asked); "
-              "oracle/nsc_oracle.py (port of the reference's Python encoder), one single-threaded process per core; "
-              "scan generation is outside the timed part")
+    sample = (f"{per_core} scans per core x {cores} cores per step; {cpu_kind_text(kind)}, one single-threaded "
+              "process per core; scan generation is outside the timed part")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": steps, "warmup": warmup, "ms_per_step": statistics.median(ms), "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.median(ms), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(N_SCANS), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": make_config(args, max(world, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
@@ -158,8 +208,165 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+# ----------------------------------------------------------------------------- GPU arm helpers
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def time_encode(enc, points, offsets, out, steps, warmup):
+    """CUDA-event time of ``steps`` launches of the fused kernel, each bracketed on the launching
+    stream; returns (mean ms per launch, total ms first-to-last)."""
+    import torch
+    dev = points.device
+    for _ in range(warmup):
+        enc.encode_points_batch(points, offsets, out=out)
+    torch.cuda.synchronize(dev)
+    stream = torch.cuda.current_stream(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps)]
+    for k in range(steps):
+        ev[2 * k].record(stream)
+        enc.encode_points_batch(points, offsets, out=out)
+        ev[2 * k + 1].record(stream)
+    torch.cuda.synchronize(dev)
+    ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(steps)]
+    return sum(ms) / len(ms), ev[0].elapsed_time(ev[-1])
+
+
+def oracle_spot_check(enc, points, offsets_host, rows, scan_ids):
+    """Rows of a timed output against the CPU oracle (the checker; never timed).
+
+    For every scan id: (1) ``rows[i]`` vs the oracle on the same cloud -- max |diff| must stay
+    below 1e-4 (points within 1e-5 rad of a pixel edge may land one pixel over, north star);
+    (2) the cloud stripped of those edge points, encoded on the GPU, vs the oracle on the
+    stripped cloud at the test-suite tolerances (rtol 1e-4 / atol 1e-7, relative L2 1e-5);
+    (3) ``rows[i]`` bit-identical to a single-scan encode of the same cloud."""
+    import numpy as np
+    from oracle import nsc_oracle as orc
+    cfg = orc.OracleConfig()
+    max_abs, max_l2, ok, same_bits = 0.0, 0.0, True, True
+    for i in scan_ids:
+        s = points[int(offsets_host[i]):int(offsets_host[i + 1])].cpu().numpy()
+        got = rows[i].cpu().numpy()
+        ref = orc.encode_points(s, cfg).numpy()
+        d = float(np.abs(got - ref).max())
+        max_abs = max(max_abs, d)
+        ok &= d < 1e-4
+        same_bits &= bool(np.array_equal(enc.encode_points(s).cpu().numpy(), got))
+        st = orc.strip_ambiguous(s, cfg)
+        g2 = enc.encode_points(st).cpu().numpy()
+        r2 = orc.encode_points(st, cfg).numpy()
+        ok &= bool(np.allclose(g2, r2, rtol=1e-4, atol=1e-7))
+        l2 = float(np.linalg.norm(g2 - r2) / max(np.linalg.norm(r2), 1e-30))
+        max_l2 = max(max_l2, l2)
+        ok &= l2 <= 1e-5
+    return {"oracle_spot": len(scan_ids), "max_abs": max_abs, "stripped_rel_l2": max_l2,
+            "rows_equal_single_scan_encode": same_bits, "ok": bool(ok and same_bits)}
+
+
+def h2d_ceiling(h_points, dev, steps, barrier):
+    """Bare pinned host -> device copy of the e2e step's bytes, nothing else in the stream: GB/s."""
+    import torch
+    d = torch.empty(h_points.shape, dtype=h_points.dtype, device=dev)
+    d.copy_(h_points, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        d.copy_(h_points, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    del d
+    return h_points.numel() * 4 * steps / dt / 1e9
+
+
+def run_other_configs(enc, dev, pool, cores, kind, peak, steps):
+    """BASELINE.json configs[2..3] and the shuffled-order variant, device-resident, at reduced
+    step counts: scans/s, roofline fraction, and the CPU encoder on the same shape."""
+    import torch
+    from neural_spectral_codec_b200 import synth
+    res = []
+    for shape, n, shuffle in (("hdl32", 4096, False), ("beam128", 2048, False), ("hdl64", 2048, True)):
+        points, offsets = synth.make_batch_resident(synth.SHAPES[shape], 0, n, dev, shuffle=shuffle)
+        out = torch.empty((n, enc.output_dim), dtype=torch.float32, device=dev)
+        ms, _ = time_encode(enc, points, offsets, out, steps, 3)
+        total_points = int(points.shape[0])
+        alg = 16 * total_points + 3200 * n
+        chk = oracle_spot_check(enc, points, offsets.cpu().numpy(), out, [0, n // 2, n - 1])
+        rec = {"workload": workload_name(n, shape, shuffle), "shape": shape, "shuffled": shuffle, "scans": n,
+               "points": total_points, "steps": steps, "kernel_ms": ms, "value": n / (ms * 1e-3), "unit": UNIT,
+               "frac": alg / (ms * 1e-3) / 1e9 / peak, "checks": chk}
+        if pool is not None:
+            v, cnt = cpu_throughput(pool, 8, cores, kind, shape, shuffle)
+            rec["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                   "sample": f"{cnt} scans (8 per core)"}
+        res.append(rec)
+        del points, offsets, out
+        torch.cuda.empty_cache()
+    return res
+
+
+def run_c5(enc, dev, rank, world, gather, total_scans, steps):
+    """BASELINE.json configs[4]: ``total_scans`` HDL-64 scans sharded over the ranks (strong
+    scaling), descriptors gathered into the database replicated on every GPU; 256 oracle spot
+    checks (every 391st scan) and a bit-comparison of every rank's database."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from neural_spectral_codec_b200 import synth
+    from neural_spectral_codec_b200.distributed import ShardedEncoder
+    from oracle import nsc_oracle as orc
+    lo, hi = synth.shard_range(total_scans, world, rank)
+    points, offsets = synth.make_batch_resident(synth.HDL64, lo, hi - lo, dev)
+    se = ShardedEncoder(enc, total_scans, mode=gather)
+    for _ in range(2):
+        se.encode(points, offsets)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        db = se.encode(points, offsets)
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # every rank's database vs an NCCL all-gather of plain single-GPU encodes of the same blocks
+    local = torch.zeros((se.per, enc.output_dim), dtype=torch.float32, device=dev)
+    enc.encode_points_batch(points, offsets, out=local[:hi - lo])
+    want = torch.empty((world * se.per, enc.output_dim), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(want, local)
+    same = torch.tensor([1 if torch.equal(want[:total_scans], db) else 0], device=dev)
+    dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    cfg = orc.OracleConfig()
+    o = offsets.cpu().numpy()
+    worst, checked = 0.0, 0
+    for g in range(0, total_scans, 391):
+        if lo <= g < hi:
+            s = points[int(o[g - lo]):int(o[g - lo + 1])].cpu().numpy()
+            worst = max(worst, float(np.abs(db[g].cpu().numpy() - orc.encode_points(s, cfg).numpy()).max()))
+            checked += 1
+    stats = torch.tensor([worst, float(checked)], dtype=torch.float64, device=dev)
+    mx = stats.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    rec = {"workload": f"{total_scans} HDL-64 scans sharded over {world} GPUs, descriptors gathered into the replicated database",
+           "scaling": "strong", "scans": total_scans, "gather": gather, "steps": steps,
+           "ms_per_pass": float(ms.item()), "value": total_scans / (float(ms.item()) * 1e-3), "unit": UNIT,
+           "points_per_gpu": int(points.shape[0]), "db_bytes": int(db.numel() * 4),
+           "db_identical": bool(int(same.item()) == 1), "oracle_spot": int(stats[1].item()),
+           "max_abs": float(mx[0].item())}
+    rec["ok"] = rec["db_identical"] and rec["max_abs"] < 1e-4
+    del points, offsets, se, db, want, local
+    torch.cuda.empty_cache()
+    return rec
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu_arm(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
 
@@ -185,9 +392,13 @@ def run_gpu_arm(args):
             pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
         except Exception:
             pass
-    if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+
+    # the CPU pool is spawned early (workers import torch while the GPU part runs)
+    pool, cores, kind = None, os.cpu_count() or 1, cpu_kind()
+    if rank == 0 and world == 1 and not args.no_cpu:
+        pool = mp.get_context("spawn").Pool(cores)
 
     n_scans = args.scans
     enc = SpectralEncoder(n_elevation=16, n_azimuth=360, n_bins=50, alpha=2.0, learnable_alpha=True,
@@ -195,12 +406,8 @@ def run_gpu_arm(args):
 
     # synthetic scans of this rank, generated on the device from per-scan seeds
     first = rank * n_scans
-    scans = [synth.make_scan(synth.SHAPES[args.shape], first + i, device=dev, shuffle=args.shuffle)
-             for i in range(n_scans)]
-    counts = torch.tensor([0] + [s.shape[0] for s in scans], dtype=torch.int64)
-    offsets = torch.cumsum(counts, 0).to(dev)
-    points = torch.cat(scans, 0)
-    del scans
+    points, offsets = synth.make_batch_resident(synth.SHAPES[args.shape], first, n_scans, dev, shuffle=args.shuffle)
+    offsets_host = offsets.cpu().numpy()
     total_points = int(points.shape[0])
     alg_bytes = 16 * total_points + 3200 * n_scans
 
@@ -256,35 +463,60 @@ def run_gpu_arm(args):
         total_ms = float(t.item())
     value = world * n_scans * args.steps / (total_ms * 1e-3)
 
-    # the fused kernel alone (same launches, N=1 path) for the roofline
-    kern_ms = step_ms
+    # the fused kernel alone (same launches, N=1 path) for the roofline; leaves the single-GPU
+    # encode of this rank's block in `out`
+    kern_avg_ms = sum(step_ms) / len(step_ms)
     if world > 1:
-        kev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
-        for k in range(args.steps):
-            kev[2 * k].record(stream)
-            enc.encode_points_batch(points, offsets, out=out)
-            kev[2 * k + 1].record(stream)
-        torch.cuda.synchronize(dev)
-        kern_ms = [kev[2 * k].elapsed_time(kev[2 * k + 1]) for k in range(args.steps)]
-    kern_avg_ms = sum(kern_ms) / len(kern_ms)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    else:
-        peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        kern_avg_ms, _ = time_encode(enc, points, offsets, out, args.steps, 0)
+    peak, peak_src = hbm_peak()
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, "not captured for this shape (ncu --set full is a separate, profiler-run pass)"
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("scans") == n_scans and args.shape == "hdl64" and not args.shuffle:
             traffic = tj.get("dram_bytes_per_launch")
+            traffic_src = ("constant read from profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one "
+                           f"ncu --set full capture of this kernel on this workload ({tj.get('source', 'see profiles/')}); "
+                           "NOT measured in this run")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "kernel": "encode_points_kernel<4,0>",
-                "kernel_ms": kern_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                "peak_source": peak_src}
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": "encode_points_ws_kernel<0>", "kernel_ms": kern_avg_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
 
-    # end to end: pinned host buffers -> descriptors on the host, through the public API
+    # ---- checks on the timed output (outside every timed region) ----------------------------------
+    checks = {}
+    ids = sorted(set(int(x) for x in np.linspace(0, n_scans - 1, 8 if world == 1 else 4)))
+    db = None
+    if sharded is not None:
+        db = sharded.db[:world * n_scans]
+        rows = db[rank * sharded.per: rank * sharded.per + n_scans]      # the timed output, this rank's block
+        want = torch.empty((world * sharded.per, enc.output_dim), dtype=torch.float32, device=dev)
+        local = torch.zeros((sharded.per, enc.output_dim), dtype=torch.float32, device=dev)
+        local[:n_scans] = out
+        dist.all_gather_into_tensor(want, local)                         # plain NCCL gather of single-GPU encodes
+        same = torch.tensor([1 if torch.equal(want[:world * n_scans], db) else 0], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        checks["db_identical"] = bool(int(same.item()) == 1)
+        del want, local
+    else:
+        rows = out
+        checks["db_identical"] = None
+    spot = oracle_spot_check(enc, points, offsets_host, rows, ids)
+    if world > 1:
+        agg = torch.tensor([spot["max_abs"], spot["stripped_rel_l2"], 0.0 if spot["ok"] else 1.0],
+                           dtype=torch.float64, device=dev)
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+        spot.update(max_abs=float(agg[0].item()), stripped_rel_l2=float(agg[1].item()), ok=bool(agg[2].item() == 0.0),
+                    oracle_spot=spot["oracle_spot"] * world)
+    checks.update(spot)
+    checks["what"] = ("rows of the timed output vs the CPU oracle on the same clouds (max_abs < 1e-4), GPU vs oracle on the "
+                      "clouds stripped of edge points (rtol 1e-4 / atol 1e-7, rel. L2 <= 1e-5), rows bit-identical to "
+                      "single-scan encodes" + ("; gathered database on every rank bit-identical to an NCCL all-gather of "
+                                               "single-GPU encodes" if world > 1 else ""))
+    checks["ok"] = bool(checks["ok"] and checks["db_identical"] is not False)
+
+    # ---- end to end: pinned host buffers -> descriptors on the host, through the public API -------
     n_e2e = min(n_scans, args.e2e_scans)
     e_off = offsets[: n_e2e + 1].cpu()
     h_points = torch.empty((int(e_off[-1]), 4), dtype=torch.float32).pin_memory()
@@ -302,49 +534,106 @@ def run_gpu_arm(args):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
+    e2e_same = bool(np.array_equal(ho, rows[:n_e2e].cpu().numpy()))
+    h2d_bytes = int(hp.nbytes + hoff.nbytes)
     e2e = {"value": world * n_e2e * e2e_steps / e2e_s, "unit": UNIT,
-           "h2d_bytes_per_step": int(hp.nbytes + hoff.nbytes), "d2h_bytes_per_step": int(ho.nbytes),
+           "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": int(ho.nbytes),
            "scans_per_step_per_gpu": n_e2e, "steps": e2e_steps,
-           "api": "SpectralEncoder.encode_scans -> nsc_pipeline_encode (pinned host buffers)"}
+           "api": "SpectralEncoder.encode_scans -> nsc_pipeline_encode (pinned host buffers)",
+           "h2d_gbs_per_gpu": h2d_bytes * e2e_steps / e2e_s / 1e9,
+           "equals_device_path": e2e_same}
+    checks["ok"] = bool(checks["ok"] and e2e_same)
+    if not args.no_extras:
+        # the ceiling: the same pinned bytes through a bare host -> device copy on every rank at once
+        ceil_gbs = h2d_ceiling(h_points, dev, e2e_steps, barrier)
+        if world > 1:
+            t = torch.tensor([ceil_gbs], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ceil_gbs = float(t.item())
+        e2e["h2d_ceiling_gbs_per_gpu"] = ceil_gbs
+        e2e["frac_of_h2d_ceiling"] = e2e["h2d_gbs_per_gpu"] / ceil_gbs
+        e2e["ceiling_note"] = ("bare cudaMemcpyAsync of the step's pinned input, all ranks at once (slowest rank); the "
+                               "end-to-end path cannot exceed it: 16 B per point have to cross PCIe")
+    if not args.no_extras and rank == 0:
+        # the reference's own call pattern (pipeline.py:336-354): one encode_points(numpy) per scan
+        host_scans = [np.array(points[int(offsets_host[i]):int(offsets_host[i + 1])].cpu().numpy()) for i in range(64)]
+        for s_ in host_scans[:4]:
+            enc.encode_points(s_).detach().cpu().numpy()
+        t0 = time.perf_counter()
+        per = [enc.encode_points(s_).detach().cpu().numpy() for s_ in host_scans]
+        dt = time.perf_counter() - t0
+        same = all(np.array_equal(per[i], rows[i].cpu().numpy()) for i in range(len(per)))
+        e2e["per_scan"] = {"value": len(host_scans) / dt, "unit": UNIT, "ms_per_scan": 1e3 * dt / len(host_scans),
+                           "scans": len(host_scans), "equals_batch_path": bool(same),
+                           "api": "encoder.encode_points(points_np).detach().cpu().numpy() per scan, pageable numpy "
+                                  "input (the reference's loop, pipeline.py:336-354)"}
+        enc.encode_scans(host_scans[:8])
+        t0 = time.perf_counter()
+        reps = 4
+        for _ in range(reps):
+            lst = enc.encode_scans(host_scans)
+        dt = time.perf_counter() - t0
+        e2e["pageable_list"] = {"value": reps * len(host_scans) / dt, "unit": UNIT, "scans": len(host_scans),
+                                "equals_batch_path": bool(np.array_equal(lst, np.stack(per))),
+                                "api": "encoder.encode_scans(list of pageable numpy scans)"}
+        checks["ok"] = bool(checks["ok"] and same)
+    del h_points, h_out
+
+    # ---- other configs (N = 1) / the sharded 100 k-scan config (N > 1) ------------------------------
+    other, c5 = None, None
+    if not args.no_extras:
+        del points, offsets, out, rows, db
+        sharded = None
+        torch.cuda.empty_cache()
+        if world == 1:
+            other = run_other_configs(enc, dev, pool, cores, kind, peak, max(3, min(args.steps, 10)))
+            checks["ok"] = bool(checks["ok"] and all(c["checks"]["ok"] for c in other))
+        else:
+            c5 = run_c5(enc, dev, rank, world, args.gather, args.c5_scans, 3)
+            checks["ok"] = bool(checks["ok"] and c5["ok"])
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
-        per_core = 64
-        v, n = cpu_oracle_throughput(per_core, cores)
+    if pool is not None:
+        per_core = 32
+        v, n = cpu_throughput(pool, per_core, cores, kind)
         # the reference's native call pattern: one process looping encode_points (pipeline.py:336-354)
-        from oracle import nsc_oracle as orc
-        cfg = orc.OracleConfig()
-        host_scans = [points[int(offsets[i]):int(offsets[i + 1])].cpu().numpy() for i in range(12)]
-        orc.encode_points(host_scans[0], cfg)
+        encode = make_cpu_encoder(kind)
+        single_scans = [synth.make_scan(synth.HDL64, 200000 + i).numpy() for i in range(12)]
+        encode(single_scans[0])
         t0 = time.perf_counter()
-        for s_ in host_scans:
-            orc.encode_points(s_, cfg)
-        single = len(host_scans) / (time.perf_counter() - t0)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{n} HDL-64 scans ({per_core} per core), oracle/nsc_oracle.py, "
+        for s_ in single_scans:
+            encode(s_)
+        single = len(single_scans) / (time.perf_counter() - t0)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": f"{n} HDL-64 scans ({per_core} per core), {cpu_kind_text(kind)}, "
                                   "one single-threaded process per core",
                         "single_process_value": single,
-                        "single_process_sample": f"{len(host_scans)} scans in one process, torch threads = "
+                        "single_process_sample": f"{len(single_scans)} scans in one process, torch threads = "
                                                  f"{torch.get_num_threads()} (the reference's per-scan loop)"}
+        pool.close()
+        pool.join()
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(n_scans, args.shape, args.shuffle), "scans_per_gpu": n_scans,
-                       "points_per_gpu": total_points, "input_bytes_per_gpu": 16 * total_points,
-                       "l2": f"inputs ({16 * total_points / 1e9:.1f} GB) larger than L2, no flush needed",
-                       "gather": ("none (single GPU)" if world == 1 else args.gather),
-                       "encoder": "n_elevation=16 n_azimuth=360 n_bins=50 alpha=2.0 target_rows=16"},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "config": make_config(args, world),
+            "workload_stats": {"points_per_gpu": total_points, "input_bytes_per_gpu": 16 * total_points},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "checks": checks,
             "gpu_launches": args.steps, "clocks": clocks,
         }
+        if other is not None:
+            line["configs"] = other
+        if c5 is not None:
+            line["c5"] = c5
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if not checks["ok"]:
+        print("[bench] CHECKS FAILED: " + json.dumps(checks), file=sys.stderr)
+        raise SystemExit(1)
 
 
 # ----------------------------------------------------------------------------- retrieval (secondary)
@@ -374,9 +663,8 @@ def run_retrieval(args):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     passes = -(-nq // 8)                                   # one pass over the CDF rows serves 8 queries
-    alg_bytes = passes * n_db * 800 * 4 + nq * n_db * 4 * 3
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else FALLBACK_HBM_GBS
+    alg_bytes = passes * n_db * 800 * 4
+    peak, _ = hbm_peak()
     line = {"metric": "retrieval_queries_per_sec_at_100k_db", "value": nq / (ms * 1e-3), "unit": "queries/s",
             "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -384,7 +672,8 @@ def run_retrieval(args):
                        "ms_per_query": ms / nq, "reference_target_ms_per_query": 27.0},
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (ms * 1e-3) / 1e9 / peak, "traffic": None,
-                         "note": "whole call (distance pass + top-K kernels + host launch gaps)"},
+                         "note": "whole call (all kernels + host launch gaps); algorithmic bytes = one pass over the "
+                                 "CDF rows per group of <= 8 queries"},
             "gpu_launches": args.steps * (passes + 1)}
     if not args.no_cpu:
         from oracle import retrieval_oracle as ro
@@ -420,8 +709,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=N_SCANS, help="scans per GPU")
     ap.add_argument("--e2e-scans", type=int, default=1024, help="scans per end-to-end step")
+    ap.add_argument("--c5-scans", type=int, default=100000, help="N > 1: total scans of the sharded config")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline line only: skip the other configs, the per-scan call pattern and the H2D ceiling")
     ap.add_argument("--shape", default="hdl64", choices=sorted(SHAPE_DESC),
                     help="sensor shape of the synthetic scans (BASELINE.json configs 2-4; default = the metric's config)")
     ap.add_argument("--shuffle", action="store_true", help="random point order inside each scan")
@@ -431,10 +723,11 @@ def main():
     ap.add_argument("--queries", type=int, default=8, help="retrieval: queries per call")
     ap.add_argument("--topk", type=int, default=10, help="retrieval: K")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
-    elif args.workload == "retrieval":
+        return
+    args.warmup = max(args.warmup, 3)
+    if args.workload == "retrieval":
         run_retrieval(args)
     else:
         run_gpu_arm(args)

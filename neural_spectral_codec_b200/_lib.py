@@ -87,14 +87,24 @@ _lib = None
 _lock = threading.Lock()
 
 
-def build(verbose: bool = False) -> str:
-    """Compile the CUDA sources for sm_100a into ``libnsc_b200.so`` (in-tree)."""
-    r = subprocess.run(["make", "-C", CSRC, "-j4"], capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        print(r.stdout)
-        print(r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("building libnsc_b200.so failed:\n" + r.stderr[-4000:])
+TUNE_LIB_PATH = os.path.join(_HERE, "libnsc_b200_tune.so")
+
+
+def build(verbose: bool = False, tuning: bool = True) -> str:
+    """Compile the CUDA sources for sm_100a into ``libnsc_b200.so`` (in-tree), and -- for the
+    A/B tools and the bit-identity tests -- the tuning build ``libnsc_b200_tune.so``
+    (``-DNSC_TUNING``: the only build that reads NSC_FEED / NSC_SPLIT / NSC_WS from the
+    environment; selected with ``NSC_LIB=<path>``)."""
+    cmds = [["make", "-C", CSRC, "-j4"]]
+    if tuning:
+        cmds.append(["make", "-C", CSRC, "-j4", "VARIANT=tune", "DEFS=-DNSC_TUNING"])
+    for cmd in cmds:
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode != 0:
+            print(r.stdout)
+            print(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("building libnsc_b200.so failed:\n" + r.stderr[-4000:])
     return LIB_PATH
 
 

@@ -395,6 +395,273 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
     }
 }
 
+// ---- warp-specialised persistent kernel ---------------------------------------------------
+// One CTA per SM. kWsStreamWarps warps only stream points and scatter; kWsTailWarps warps only
+// run the tail (ranges, interpolation, FFT, bins, normalisation) of the scan the stream warps
+// finished before, from the other of two shared-memory images. The stream warps never wait for
+// a tail, and their cp.async ring keeps flowing across scan boundaries: the first stages of the
+// next scan are issued while the last stages of the current one are consumed (every scan is
+// padded to a multiple of kWsDepth stages so ring slots stay compile-time offsets).
+//
+// Hand-off through named barriers (bar.arrive by the producer side, bar.sync by the consumer
+// side, count = all threads of the CTA):
+//   kBarFull + b   stream warps arrive when image b holds a complete scan; tail warps wait
+//   kBarEmpty + b  tail warps arrive when image b is re-initialised; stream warps wait
+//   kBarTail       barrier of the tail group alone
+#ifndef NSC_WS_STREAM_WARPS
+#define NSC_WS_STREAM_WARPS 24
+#endif
+#ifndef NSC_WS_TAIL_WARPS
+#define NSC_WS_TAIL_WARPS 8
+#endif
+#ifndef NSC_WS_DEPTH
+#define NSC_WS_DEPTH 5
+#endif
+constexpr int kWsStreamWarps = NSC_WS_STREAM_WARPS;
+constexpr int kWsTailWarps = NSC_WS_TAIL_WARPS;
+constexpr int kWsStreamThreads = kWsStreamWarps * 32;
+constexpr int kWsTailThreads = kWsTailWarps * 32;
+constexpr int kWsThreads = kWsStreamThreads + kWsTailThreads;
+constexpr int kWsDepth = NSC_WS_DEPTH;
+constexpr int kWsStagePoints = kCpPts * kWsStreamThreads;
+constexpr int kWsSlotBytes = kWsStagePoints * 16;
+constexpr int kBarTail = 1, kBarFull = 2, kBarEmpty = 4;
+using TailGroup = ThreadGroup<kWsTailThreads, kBarTail, kWsStreamThreads>;
+static_assert(kWsThreads <= 1024 && kWsTailWarps <= kWarps, "warp split");
+
+struct WsLayout {
+    int img_off[2], tw_off, fa_off, hist_off, mask_off, nvalid_off, src_off, red_off, bins_off;
+    int mail_off, ring_off, total, img_words;
+    bool ok;       // false: this geometry needs the generic kernel
+    __host__ __device__ WsLayout(int rows, int T, int n_bins) {
+        int o = 0;
+        auto take = [&o](int bytes) { int r = o; o += (bytes + 127) & ~127; return r; };
+        const int n_sig = (T + 1) / 2;
+        ok = n_sig <= kMaxSignals;
+        const int sig_bytes = (n_sig < kMaxSignals ? n_sig : kMaxSignals) * kAz * 8;
+        // an image doubles as the second FFT buffer of its own tail
+        const int img_bytes = rows * kPitch * 4 > sig_bytes ? rows * kPitch * 4 : sig_bytes;
+        img_words = rows * kPitch;
+        img_off[0] = take(img_bytes);
+        img_off[1] = take(img_bytes);
+        tw_off = take(kAz * 8);
+        fa_off = take(sig_bytes);
+        hist_off = take(T * n_bins * 4);
+        mask_off = take(rows * kMaskWords * 4);
+        nvalid_off = take(rows * 4);
+        src_off = take(rows * 4);
+        red_off = take(kWarps * 8 + 16);
+        bins_off = take(NSC_MAX_BINS + 3);
+        mail_off = take(16);
+        ring_off = take(kWsDepth * kWsSlotBytes);
+        total = o;
+    }
+};
+
+__device__ __forceinline__ void bar_sync_all(int id) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kWsThreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_all(int id) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kWsThreads) : "memory");
+}
+
+// One scan of `n` points at gp (already offset by the thread index) through this thread's ring
+// into the image behind img_biased. Stages 0 .. kWsDepth-2 of the scan are in flight on entry;
+// on return the same holds for the next scan (gpn, nn).
+template <int ROWMODE>
+__device__ __forceinline__ void ws_stream_scan(const float4* __restrict__ gp, int n,
+                                               const float4* __restrict__ gpn, int nn,
+                                               uint32_t ring_t, uint32_t img_biased,
+                                               const DeviceParams& dp) {
+    constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
+    const int tid = threadIdx.x;
+    const int n_full = n / SP;
+    const int n_iter = (n + SP - 1) / SP;
+    int P = ((n_iter + D - 1) / D) * D;       // stages of this scan, padded (>= D: the loop below
+    if (P < D) P = D;                         // must issue the whole prologue of the next scan)
+    auto issue = [&](int j) {                 // stage j of this scan, or stage j - P of the next
+        const bool nx = j >= P;
+        const float4* base = nx ? gpn : gp;
+        const int m = nx ? nn : n;
+        const int jj = nx ? j - P : j;
+        const uint32_t dst = ring_t + (uint32_t)(j % D) * SLOT;
+#pragma unroll
+        for (int u = 0; u < kCpPts; ++u) {
+            const int i = jj * SP + u * NT;
+            if (i + tid < m) cp_async16(dst + u * (NT * 16), base + i);
+        }
+        cp_async_commit();
+    };
+    int it = 0;
+    for (; it + 2 * D - 2 < n_full; it += D) {          // every stage touched is full
+        const float4* g = gp + (long long)it * SP;
+#pragma unroll
+        for (int s = 0; s < D; ++s) {
+#pragma unroll
+            for (int u = 0; u < kCpPts; ++u)
+                cp_async16(ring_t + ((s + D - 1) % D) * SLOT + u * (NT * 16),
+                           g + (s + D - 1) * SP + u * NT);
+            cp_async_commit();
+            cp_async_wait<D - 1>();
+            float4 v[kCpPts];
+#pragma unroll
+            for (int u = 0; u < kCpPts; ++u) v[u] = lds128(ring_t + s * SLOT + u * (NT * 16));
+#pragma unroll
+            for (int u = 0; u < kCpPts; ++u)
+                project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+        }
+    }
+    for (; it < P; ++it) {
+        issue(it + D - 1);
+        cp_async_wait<D - 1>();
+        if (it < n_iter) {
+            const uint32_t src = ring_t + (uint32_t)(it % D) * SLOT;
+#pragma unroll
+            for (int u = 0; u < kCpPts; ++u) {
+                const int i = it * SP + u * NT + tid;
+                const float4 v = lds128(src + u * (NT * 16));
+                project_point<ROWMODE>(v.x, v.y, v.z, dp, img_biased, i < n);
+            }
+        }
+    }
+}
+
+template <int ROWMODE>
+__device__ __forceinline__ void ws_stream_role(const EncodeArgs& a, const DeviceParams& dp,
+                                               unsigned char* smem, const WsLayout& L) {
+    constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
+    const int tid = threadIdx.x;
+    const uint32_t ring_t = smem_u32(smem + L.ring_off) + tid * 16;
+    volatile int* mail = reinterpret_cast<volatile int*>(smem + L.mail_off);
+    const uint32_t bias = kFloorBias * (uint32_t)(kPitch * 4 + 4);
+    const uint32_t img_b0 = smem_u32(smem + L.img_off[0]) - bias, img_b1 = smem_u32(smem + L.img_off[1]) - bias;
+    const float4* p4 = reinterpret_cast<const float4*>(a.points);
+    // The first scan of a CTA is its block index; later ones come from the work counter, fetched
+    // by thread 0 one scan ahead and handed to the other stream threads through mail[0..1].
+    int cur = blockIdx.x;
+    int fetched = 0;
+    if (tid == 0) fetched = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
+    int n = 0;
+    const float4* gp = p4 + tid;
+    if (cur < a.n_scans) {
+        const long long o0 = a.offsets[cur];
+        gp += o0 - a.origin;
+        n = (int)(a.offsets[cur + 1] - o0);
+    }
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) {
+#pragma unroll
+        for (int u = 0; u < kCpPts; ++u) {
+            const int i = d * SP + u * NT;
+            if (i + tid < n) cp_async16(ring_t + d * SLOT + u * (NT * 16), gp + i);
+        }
+        cp_async_commit();
+    }
+    for (int k = 0;; ++k) {
+        const int b = k & 1;
+        if (tid == 0) mail[b ^ 1] = fetched;              // scan k + 1
+        bar_sync_all(kBarEmpty + b);                       // image b is free (and mail is visible)
+        if (cur >= a.n_scans) {
+            if (tid == 0) mail[2 + b] = -1;
+            bar_arrive_all(kBarFull + b);                  // tells the tail group to stop
+            bar_sync_all(kBarEmpty + (b ^ 1));             // consume its last arrival
+            break;
+        }
+        const int nxt = mail[b ^ 1];
+        if (tid == 0) fetched = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);   // scan k + 2
+        int nn = 0;
+        const float4* gpn = p4 + tid;
+        if (nxt < a.n_scans) {
+            const long long o0 = a.offsets[nxt];
+            gpn += o0 - a.origin;
+            nn = (int)(a.offsets[nxt + 1] - o0);
+        }
+        ws_stream_scan<ROWMODE>(gp, n, gpn, nn, ring_t, b ? img_b1 : img_b0, dp);
+        if (tid == 0) mail[2 + b] = cur;
+        bar_arrive_all(kBarFull + b);
+        cur = nxt;
+        gp = gpn;
+        n = nn;
+    }
+    cp_async_wait<0>();
+}
+
+__device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DeviceParams& dp,
+                                             unsigned char* smem, const WsLayout& L) {
+    using G = TailGroup;
+    const int gt = G::tid();
+    volatile int* mail = reinterpret_cast<volatile int*>(smem + L.mail_off);
+    TailSmem S;
+    S.tw = (float2*)(smem + L.tw_off);
+    S.fa = (float2*)(smem + L.fa_off);
+    S.hist = (float*)(smem + L.hist_off);
+    S.mask = (uint32_t*)(smem + L.mask_off);
+    S.nvalid = (int*)(smem + L.nvalid_off);
+    S.src = (int*)(smem + L.src_off);
+    S.red = (double*)(smem + L.red_off);
+    S.bin_start = smem + L.bins_off;
+    const int D = dp.T * dp.n_bins;
+    bar_arrive_all(kBarEmpty + 0);
+    bar_arrive_all(kBarEmpty + 1);
+    for (int k = 0;; ++k) {
+        const int b = k & 1;
+        bar_sync_all(kBarFull + b);
+        const int scan = mail[2 + b];
+        if (scan < 0) break;
+        S.img = (float*)(smem + (b ? L.img_off[1] : L.img_off[0]));
+        S.fb = (float2*)S.img;
+        uint32_t* img = reinterpret_cast<uint32_t*>(S.img);
+        // the image is dead once the magnitudes are out of it: hand it back to the stream warps
+        auto release = [&]() {
+            for (int i = gt; i < L.img_words; i += G::kSize) img[i] = kInfBits;
+            bar_arrive_all(kBarEmpty + b);
+        };
+        float* stage0 = (a.img_out && a.stage == NSC_STAGE_PROJECTED)
+                            ? a.img_out + (long long)scan * dp.E * kAz : nullptr;
+        rows_to_filled<true, G>(S, dp.E, dp.interpolate != 0, stage0, [&dp](uint32_t key) {
+            return key_is_empty(key, dp) ? 0.0f : __fsqrt_rn(__uint_as_float(key));
+        });
+        if (a.img_out && a.stage == NSC_STAGE_INTERPOLATED) {
+            for (int i = gt; i < dp.E * kAz; i += G::kSize) {
+                const int r = i / kAz, c = i - r * kAz;
+                a.img_out[(long long)scan * dp.E * kAz + i] = S.img[S.src[r] * kPitch + c];
+            }
+        }
+        if (a.out || a.peers.n > 0) {
+            spectrum_and_bins(S, dp, dp.E, [&](int p) { if (p == 9) release(); }, G());
+            normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
+                                a.peers.row0 + scan, G());
+            // S.red / S.hist / S.src are next written after the kBarFull wait above, which every
+            // thread of this group has to reach first
+        } else {
+            G::sync();     // every thread is done reading the image
+            release();
+        }
+    }
+}
+
+template <int ROWMODE>
+__global__ void __launch_bounds__(kWsThreads, 1)
+encode_points_ws_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const WsLayout L(dp.E, dp.T, dp.n_bins);
+    {
+        TailSmem S;
+        S.tw = (float2*)(smem_raw + L.tw_off);
+        S.bin_start = smem_raw + L.bins_off;
+        init_tail_tables(S, dp);
+        uint32_t* i0 = reinterpret_cast<uint32_t*>(smem_raw + L.img_off[0]);
+        uint32_t* i1 = reinterpret_cast<uint32_t*>(smem_raw + L.img_off[1]);
+        for (int i = threadIdx.x; i < L.img_words; i += kWsThreads) {
+            i0[i] = kInfBits;
+            i1[i] = kInfBits;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < kWsStreamThreads) ws_stream_role<ROWMODE>(a, dp, smem_raw, L);
+    else ws_tail_role(a, dp, smem_raw, L);
+}
+
 // Small batches (fewer scans than SMs / cluster size): one thread-block CLUSTER per scan. The
 // CTAs of a cluster each scatter a contiguous slice of the scan into their own shared-memory
 // image; after a cluster barrier the leader min-reduces the other images through distributed
@@ -584,21 +851,26 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     a.peers.row0 = peer_row0;
     for (int i = 0; i < NSC_MAX_PEERS; ++i) a.peers.ptr[i] = i < n_peers ? d_peer_out[i] : nullptr;
 
-    // Feed of the point pass (see enum Feed). NSC_FEED=ldg|cpasync overrides for A/B runs.
+    // Feed of the point pass (see enum Feed) and kernel choice. Product builds take no switches;
+    // tuning builds (-DNSC_TUNING, csrc/Makefile VARIANT=tune) read NSC_FEED=ldg|cpasync|tma,
+    // NSC_SPLIT=0 and NSC_WS=0 from the environment, once, for A/B runs and the bit-identity tests.
+    int feed = kDefaultFeed;
+    bool split_allowed = true, ws_allowed = true;
+#ifdef NSC_TUNING
     static const int feed_override = [] {
         const char* e = getenv("NSC_FEED");
         if (!e) return -1;
         return strcmp(e, "ldg") == 0 ? (int)kFeedLdg : strcmp(e, "cpasync") == 0 ? (int)kFeedCpAsync
                : strcmp(e, "tma") == 0 ? (int)kFeedTma : -1;
     }();
-    int feed = feed_override >= 0 ? feed_override : kDefaultFeed;
+    static const bool env_split = [] { const char* e = getenv("NSC_SPLIT"); return !(e && e[0] == '0'); }();
+    static const bool env_ws = [] { const char* e = getenv("NSC_WS"); return !(e && e[0] == '0'); }();
+    if (feed_override >= 0) feed = feed_override;
+    split_allowed = env_split;
+    ws_allowed = env_ws && feed_override < 0;
+#endif
     if (stride != 4) feed = kFeedLdg;
     const SmemLayout L(dp.E, dp.T, dp.n_bins, ring_bytes_of(feed));
-    // Few scans: one cluster of 2/4/8 CTAs per scan (NSC_SPLIT=0 disables, for A/B runs).
-    static const bool split_allowed = [] {
-        const char* e = getenv("NSC_SPLIT");
-        return !(e && e[0] == '0');
-    }();
     int csize = 1;
     if (split_allowed) {
         if (n_scans * 8 <= di.sms) csize = 8;
@@ -635,6 +907,19 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         return record_cuda(cudaLaunchKernelEx(&cfg, kernel, a, dp));
+    }
+    // Large batches of 16-byte points: the warp-specialised kernel, when two images, the FFT
+    // scratch and the ring fit one SM's shared memory; other geometries take the generic kernel.
+    const WsLayout W(dp.E, dp.T, dp.n_bins);
+    if (ws_allowed && stride == 4 && W.ok && W.total <= di.max_smem_optin) {
+        kernel = poly ? encode_points_ws_kernel<kRowPoly> : encode_points_ws_kernel<kRowSearch>;
+        st = configure(kernel, W.total, di, nullptr);
+        if (st != NSC_OK) return st;
+        cudaError_t e = cudaMemsetAsync(d_workspace, 0, 2 * sizeof(unsigned), stream);
+        if (e != cudaSuccess) return record_cuda(e);
+        const int grid = di.sms < n_scans ? di.sms : n_scans;
+        kernel<<<grid, kWsThreads, W.total, stream>>>(a, dp);
+        return record_cuda(cudaGetLastError());
     }
     if (feed == kFeedTma) {
         kernel = poly ? encode_points_kernel<4, kRowPoly, kFeedTma>

@@ -20,6 +20,20 @@ constexpr int kThreads = NSC_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMinBlocks = NSC_MIN_BLOCKS;   // resident CTAs per SM the kernels are compiled for
 
+// The threads that run the tail together: the whole CTA (BAR = 0, __syncthreads), or a warp
+// group of a warp-specialised CTA meeting on its own named barrier (encode_points_ws_kernel).
+template <int SIZE, int BAR, int TID0>
+struct ThreadGroup {
+    static constexpr int kSize = SIZE;
+    static constexpr int kGroupWarps = SIZE / 32;
+    __device__ static __forceinline__ int tid() { return (int)threadIdx.x - TID0; }
+    __device__ static __forceinline__ void sync() {
+        if (BAR == 0) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(SIZE) : "memory");
+    }
+};
+using CtaGroup = ThreadGroup<kThreads, 0, 0>;
+
 // Per-thread cp.async ring (LDGSTS feed): kCpDepth stages of kCpPts 16-byte points per thread.
 #ifndef NSC_CP_PTS
 #define NSC_CP_PTS 2
@@ -73,6 +87,7 @@ struct TailSmem {
     int* src;          // row r of the filled image is stored row src[r]
     double* red;
     uint8_t* bin_start;  // copy of DeviceParams::bin_start: per-thread indices would serialise in the constant bank
+    __device__ TailSmem() {}
     __device__ TailSmem(unsigned char* base, const SmemLayout& L)
         : img((float*)(base + L.img_off)), tw((float2*)(base + L.tw_off)),
           fa((float2*)(base + L.fa_off)), fb((float2*)(base + L.fb_off)),
@@ -84,12 +99,13 @@ struct TailSmem {
 // Per-CTA constants of the tail: FFT twiddles and the bin boundaries.
 template <typename P>
 __device__ __forceinline__ void init_tail_tables(const TailSmem& S, const P& dp) {
-    for (int m = threadIdx.x; m < kAz; m += kThreads) {
+    const int n_thr = (int)blockDim.x;
+    for (int m = threadIdx.x; m < kAz; m += n_thr) {
         float s, c;
         sincospif((float)m * (1.0f / 180.0f), &s, &c);   // angle = 2 pi m / 360
         S.tw[m] = make_float2(c, -s);
     }
-    for (int b = threadIdx.x; b <= dp.n_bins; b += kThreads) S.bin_start[b] = dp.bin_start[b];
+    for (int b = threadIdx.x; b <= dp.n_bins; b += n_thr) S.bin_start[b] = dp.bin_start[b];
 }
 
 // Nearest valid column strictly left / right of x on the circular row; the returned position
@@ -120,11 +136,11 @@ __device__ __forceinline__ int next_valid(const uint32_t* m, int x) {
 // so no block barrier separates the three steps. FROM_KEYS: the row holds the bits of the min
 // of s per pixel (plus the 361st column for azimuth == 2 pi); `to_value(key)` maps them to ranges.
 // `stage0`, if not null, receives the un-interpolated rows (rows x 360, global memory).
-template <bool FROM_KEYS, typename ToValue>
+template <bool FROM_KEYS, typename G = CtaGroup, typename ToValue>
 __device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool interpolate,
                                                float* __restrict__ stage0, ToValue to_value) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int r = warp; r < rows; r += kWarps) {
+    const int warp = G::tid() >> 5, lane = G::tid() & 31;
+    for (int r = warp; r < rows; r += G::kGroupWarps) {
         float* row = S.img + r * kPitch;
         uint32_t* m = S.mask + r * kMaskWords;
         int cnt = 0;
@@ -162,12 +178,12 @@ __device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool
             }
         }
     }
-    __syncthreads();
+    G::sync();
     // Empty-row fill (range_image.py:77-87) as a row indirection src[] instead of copies: rows with
     // no pixel > 0 take the nearest filled row below, leading ones the first non-empty row above;
     // an all-empty image stays zero (the sequential in-place semantics of the reference).
-    if (threadIdx.x < rows) {
-        const int r = threadIdx.x;
+    if (G::tid() < rows) {
+        const int r = G::tid();
         int s = r;
         if (interpolate && S.nvalid[r] == 0) {
             int k = r - 1;
@@ -180,7 +196,7 @@ __device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool
         }
         S.src[r] = s;
     }
-    __syncthreads();
+    G::sync();
 }
 
 // Value of target row i at column n: the stored row, or the mean of its source rows when the
@@ -195,11 +211,11 @@ __device__ __forceinline__ float pooled_value(const TailSmem& S, int rows, int T
 
 // One Stockham pass of radix R over n_sig complex signals of length 360: one thread per
 // butterfly (nsc_fft.cuh), R inputs and outputs in registers.
-template <int R, int NS>
+template <int R, int NS, typename G = CtaGroup>
 __device__ __forceinline__ void fft_pass(const float2* __restrict__ x, float2* __restrict__ y,
                                          const float2* __restrict__ tw, int n_sig) {
     constexpr int kBfly = kAz / R;
-    for (int t = threadIdx.x; t < n_sig * kBfly; t += kThreads) {
+    for (int t = G::tid(); t < n_sig * kBfly; t += G::kSize) {
         const int g = t / kBfly, j = t - g * kBfly;
         stockham_butterfly<R, NS>(x + g * kAz, y + g * kAz, tw, j);
     }
@@ -213,36 +229,36 @@ struct NoMark {
 };
 // `mark(p)` is a tuning hook called by thread-uniform code between the sub-phases (5 = signals
 // loaded, 6..8 = after each FFT pass, 9 = magnitudes); a no-op in product builds.
-template <typename P, typename Mark = NoMark>
+template <typename P, typename Mark = NoMark, typename G = CtaGroup>
 __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp, int rows,
-                                                  Mark mark = Mark()) {
+                                                  Mark mark = Mark(), G = G()) {
     const int T = dp.T, nb = dp.n_bins;
     const int n_sig_total = (T + 1) / 2;
     const int cap = n_sig_total < kMaxSignals ? n_sig_total : kMaxSignals;
     float* mag = reinterpret_cast<float*>(S.fa);           // 2 * n_sig x 181, valid after the last pass
     for (int g0 = 0; g0 < n_sig_total; g0 += cap) {
         const int n_sig = min(cap, n_sig_total - g0);
-        for (int t = threadIdx.x; t < n_sig * kAz; t += kThreads) {
+        for (int t = G::tid(); t < n_sig * kAz; t += G::kSize) {
             const int g = t / kAz, n = t - g * kAz;
             const int ra = 2 * (g0 + g), rb = ra + 1;
             const float a = pooled_value(S, rows, T, ra, n);
             const float b = rb < T ? pooled_value(S, rows, T, rb, n) : 0.0f;
             S.fa[t] = make_float2(a, b);
         }
-        __syncthreads();
+        G::sync();
         mark(5);
-        fft_pass<8, 1>(S.fa, S.fb, S.tw, n_sig);
-        __syncthreads();
+        fft_pass<8, 1, G>(S.fa, S.fb, S.tw, n_sig);
+        G::sync();
         mark(6);
-        fft_pass<9, 8>(S.fb, S.fa, S.tw, n_sig);
-        __syncthreads();
+        fft_pass<9, 8, G>(S.fb, S.fa, S.tw, n_sig);
+        G::sync();
         mark(7);
-        fft_pass<5, 72>(S.fa, S.fb, S.tw, n_sig);
-        __syncthreads();
+        fft_pass<5, 72, G>(S.fa, S.fb, S.tw, n_sig);
+        G::sync();
         mark(8);
         // Z = FFT(a + i b): A[k] = (Z[k] + conj Z[-k]) / 2, B[k] = (Z[k] - conj Z[-k]) / 2i; one
         // thread per (signal, frequency), both magnitudes (fa is free again: the spectrum is in fb)
-        for (int t = threadIdx.x; t < n_sig * kFreqs; t += kThreads) {
+        for (int t = G::tid(); t < n_sig * kFreqs; t += G::kSize) {
             const int g = t / kFreqs, k = t - g * kFreqs;
             const float2* z = S.fb + g * kAz;
             const float2 p = z[k], m = z[k == 0 ? 0 : kAz - k];
@@ -251,11 +267,11 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
             mag[(2 * g) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(ar, ar, ai * ai));
             mag[(2 * g + 1) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(br, br, bi * bi));
         }
-        __syncthreads();
+        G::sync();
         mark(9);
         // contiguous-frequency bin sums in ascending k: the CPU order of scatter_add_
         const int row0 = 2 * g0, row1 = min(T, 2 * (g0 + n_sig));
-        for (int i = threadIdx.x; i < T * nb; i += kThreads) {
+        for (int i = G::tid(); i < T * nb; i += G::kSize) {
             const int r = i / nb, b = i - r * nb;
             if (r < row0 || r >= row1) continue;
             const float* mr = mag + (r - row0) * kFreqs;
@@ -263,7 +279,7 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
             for (int k = S.bin_start[b], k1 = S.bin_start[b + 1]; k < k1; ++k) h += mr[k];
             S.hist[i] = h;
         }
-        if (g0 + cap < n_sig_total) __syncthreads();   // the next batch overwrites fa / fb
+        if (g0 + cap < n_sig_total) G::sync();   // the next batch overwrites fa / fb
     }
 }
 
@@ -274,24 +290,24 @@ struct PeerOut {
     long long row0;
 };
 
-template <typename P>
+template <typename P, typename G = CtaGroup>
 __device__ __forceinline__ void normalise_and_store(const TailSmem& S, const P& dp, float* out,
-                                                    const PeerOut& peers, long long peer_row) {
+                                                    const PeerOut& peers, long long peer_row, G = G()) {
     const int D = dp.T * dp.n_bins;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = G::tid() >> 5, lane = G::tid() & 31;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < D; i += kThreads) acc += (double)S.hist[i];   // own entries only
+    for (int i = G::tid(); i < D; i += G::kSize) acc += (double)S.hist[i];   // own entries only
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
     if (lane == 0) S.red[warp] = acc;
-    __syncthreads();
+    G::sync();
     double tot = 0.0;
 #pragma unroll
-    for (int w = 0; w < kWarps; ++w) tot += S.red[w];
+    for (int w = 0; w < G::kGroupWarps; ++w) tot += S.red[w];
     const float total = (float)tot;
     const bool ok = total > dp.eps;
     const float denom = __fadd_rn(total, dp.eps);
-    for (int i = threadIdx.x; i < D; i += kThreads) {
+    for (int i = G::tid(); i < D; i += G::kSize) {
         const float v = ok ? __fdiv_rn(S.hist[i], denom) : dp.uniform;
         if (out) out[i] = v;
         for (int p = 0; p < peers.n; ++p) peers.ptr[p][peer_row * D + i] = v;

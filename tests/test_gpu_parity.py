@@ -393,14 +393,16 @@ def test_plain_c_caller_runs():
         assert r.stdout.count("descriptor sum 1.0000") + r.stdout.count("descriptor sum 0.9999") == 2, r.stdout
 
 
-@pytest.mark.parametrize("feed", ["tma", "ldg"])
+@pytest.mark.parametrize("feed", ["tma", "ldg", "cpasync", "ws0"])
 def test_alternative_feeds_give_the_same_bits(feed, tmp_path):
-    """The point pass can be fed by cp.async (default), by whole-stage TMA bulk copies with a
-    producer warp, or by plain vector loads (NSC_FEED, read once per process): same descriptors."""
+    """Large batches run the warp-specialised kernel (stream warps + tail warps, two images).
+    The tuning build (libnsc_b200_tune.so, the only one that reads the environment) can instead
+    run the generic persistent kernel fed by cp.async, by whole-stage TMA bulk copies with a
+    producer warp, or by plain vector loads: same descriptors, bit for bit."""
     import subprocess
     import sys
     from conftest import ROOT
-    from neural_spectral_codec_b200 import synth
+    from neural_spectral_codec_b200 import _lib, synth
     small = synth.SensorShape("s", 64, -24.8, 2.0, 700)
     enc = make_encoder()
     want = {}
@@ -421,7 +423,8 @@ for n in (2, 170):
 print("same")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
-                       env=dict(os.environ, NSC_FEED=feed), timeout=600)
+                       env=dict(os.environ, NSC_LIB=_lib.TUNE_LIB_PATH,
+                                **({"NSC_WS": "0"} if feed == "ws0" else {"NSC_FEED": feed})), timeout=600)
     assert r.returncode == 0 and "same" in r.stdout, r.stderr[-2000:]
 
 
