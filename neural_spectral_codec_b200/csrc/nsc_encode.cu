@@ -102,6 +102,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
+// Same with an L2 cache-policy operand (createpolicy evict_first: the points are read once).
+#ifdef NSC_CP_EVICT_FIRST
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+#endif
+__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, uint64_t pol) {
+#ifdef NSC_CP_EVICT_FIRST
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol)
+                 : "memory");
+#else
+    (void)pol;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+#endif
+}
 __device__ __forceinline__ void cp_async_commit() {
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -152,10 +169,15 @@ __device__ __forceinline__ void scatter_min(uint32_t img_biased, uint32_t row_b,
 template <int ROWMODE>
 __device__ __forceinline__ void project_point(float x, float y, float z, const DeviceParams& dp,
                                               uint32_t img_biased, bool in_range = true) {
+#ifdef NSC_EXP_NO_COMPUTE
+    // measurement-only build: keeps the loads alive, does no arithmetic and (in practice) no scatter
+    if (x == 12345.678f && in_range) scatter_min(img_biased, kFloorBias, kFloorBias, __float_as_uint(y + z));
+#else
     uint32_t row_b, col_b;
     uint32_t key = classify(x, y, z, dp, ROWMODE, row_b, col_b);
     if (!in_range) key = 0xffffffffu;
     scatter_min(img_biased, row_b, col_b, key);
+#endif
 }
 
 // Point pass over points [beg, beg + n) of the concatenated buffer: every kept point lowers the
@@ -403,11 +425,15 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
 // next scan are issued while the last stages of the current one are consumed (every scan is
 // padded to a multiple of kWsDepth stages so ring slots stay compile-time offsets).
 //
-// Hand-off through named barriers (bar.arrive by the producer side, bar.sync by the consumer
-// side, count = all threads of the CTA):
-//   kBarFull + b   stream warps arrive when image b holds a complete scan; tail warps wait
-//   kBarEmpty + b  tail warps arrive when image b is re-initialised; stream warps wait
-//   kBarTail       barrier of the tail group alone
+// Hand-off through four mbarriers, so that no stream warp ever waits for another stream warp:
+//   full[b]   one arrival per stream warp when its share of the scan is in image b; the tail
+//             warps wait for the phase of scan k (parity (k >> 1) & 1)
+//   empty[b]  one arrival per tail warp when image b is re-initialised; a stream warp waits for
+//             it before its first scatter of scan k >= 2 (parity ((k >> 1) - 1) & 1)
+// Scan indices: the k-th scan of a CTA is its block index for k = 0 and comes from the work
+// counter afterwards, fetched by thread 0 two scans ahead and published in mail[k & 3] as
+// (sequence k, scan index); readers spin until the sequence matches (it practically always does).
+// An index >= n_scans ends both roles. kBarTail is the named barrier of the tail group alone.
 #ifndef NSC_WS_STREAM_WARPS
 #define NSC_WS_STREAM_WARPS 24
 #endif
@@ -425,13 +451,13 @@ constexpr int kWsThreads = kWsStreamThreads + kWsTailThreads;
 constexpr int kWsDepth = NSC_WS_DEPTH;
 constexpr int kWsStagePoints = kCpPts * kWsStreamThreads;
 constexpr int kWsSlotBytes = kWsStagePoints * 16;
-constexpr int kBarTail = 1, kBarFull = 2, kBarEmpty = 4;
+constexpr int kBarTail = 1;
 using TailGroup = ThreadGroup<kWsTailThreads, kBarTail, kWsStreamThreads>;
 static_assert(kWsThreads <= 1024 && kWsTailWarps <= kWarps, "warp split");
 
 struct WsLayout {
     int img_off[2], tw_off, fa_off, hist_off, mask_off, nvalid_off, src_off, red_off, bins_off;
-    int mail_off, ring_off, total, img_words;
+    int mail_off, mbar_off, ring_off, total, img_words;
     bool ok;       // false: this geometry needs the generic kernel
     __host__ __device__ WsLayout(int rows, int T, int n_bins) {
         int o = 0;
@@ -452,17 +478,21 @@ struct WsLayout {
         src_off = take(rows * 4);
         red_off = take(kWarps * 8 + 16);
         bins_off = take(NSC_MAX_BINS + 3);
-        mail_off = take(16);
+        mail_off = take(4 * 8);
+        mbar_off = take(4 * 8);
         ring_off = take(kWsDepth * kWsSlotBytes);
         total = o;
     }
 };
 
-__device__ __forceinline__ void bar_sync_all(int id) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kWsThreads) : "memory");
+// mail entry: (sequence << 32) | scan index, one aligned 64-bit shared-memory word
+__device__ __forceinline__ void mail_write(volatile long long* mail, int k, int scan) {
+    mail[k & 3] = ((long long)k << 32) | (unsigned)scan;
 }
-__device__ __forceinline__ void bar_arrive_all(int id) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(kWsThreads) : "memory");
+__device__ __forceinline__ int mail_read(const volatile long long* mail, int k) {
+    long long v;
+    do v = mail[k & 3]; while ((int)(v >> 32) != k);
+    return (int)(unsigned)v;
 }
 
 // One scan of `n` points at gp (already offset by the thread index) through this thread's ring
@@ -472,7 +502,7 @@ template <int ROWMODE>
 __device__ __forceinline__ void ws_stream_scan(const float4* __restrict__ gp, int n,
                                                const float4* __restrict__ gpn, int nn,
                                                uint32_t ring_t, uint32_t img_biased,
-                                               const DeviceParams& dp) {
+                                               const DeviceParams& dp, uint64_t pol) {
     constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
     const int tid = threadIdx.x;
     const int n_full = n / SP;
@@ -488,7 +518,7 @@ __device__ __forceinline__ void ws_stream_scan(const float4* __restrict__ gp, in
 #pragma unroll
         for (int u = 0; u < kCpPts; ++u) {
             const int i = jj * SP + u * NT;
-            if (i + tid < m) cp_async16(dst + u * (NT * 16), base + i);
+            if (i + tid < m) cp_async16_hint(dst + u * (NT * 16), base + i, pol);
         }
         cp_async_commit();
     };
@@ -499,8 +529,8 @@ __device__ __forceinline__ void ws_stream_scan(const float4* __restrict__ gp, in
         for (int s = 0; s < D; ++s) {
 #pragma unroll
             for (int u = 0; u < kCpPts; ++u)
-                cp_async16(ring_t + ((s + D - 1) % D) * SLOT + u * (NT * 16),
-                           g + (s + D - 1) * SP + u * NT);
+                cp_async16_hint(ring_t + ((s + D - 1) % D) * SLOT + u * (NT * 16),
+                                g + (s + D - 1) * SP + u * NT, pol);
             cp_async_commit();
             cp_async_wait<D - 1>();
             float4 v[kCpPts];
@@ -528,47 +558,23 @@ __device__ __forceinline__ void ws_stream_scan(const float4* __restrict__ gp, in
 
 template <int ROWMODE>
 __device__ __forceinline__ void ws_stream_role(const EncodeArgs& a, const DeviceParams& dp,
-                                               unsigned char* smem, const WsLayout& L) {
-    constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
+                                               unsigned char* smem, const WsLayout& L,
+                                               const float4* gp, int n, int pending, uint64_t pol) {
     const int tid = threadIdx.x;
     const uint32_t ring_t = smem_u32(smem + L.ring_off) + tid * 16;
-    volatile int* mail = reinterpret_cast<volatile int*>(smem + L.mail_off);
+    volatile long long* mail = reinterpret_cast<volatile long long*>(smem + L.mail_off);
+    const uint32_t bars = smem_u32(smem + L.mbar_off);     // full[0], full[1], empty[0], empty[1]
     const uint32_t bias = kFloorBias * (uint32_t)(kPitch * 4 + 4);
     const uint32_t img_b0 = smem_u32(smem + L.img_off[0]) - bias, img_b1 = smem_u32(smem + L.img_off[1]) - bias;
     const float4* p4 = reinterpret_cast<const float4*>(a.points);
-    // The first scan of a CTA is its block index; later ones come from the work counter, fetched
-    // by thread 0 one scan ahead and handed to the other stream threads through mail[0..1].
     int cur = blockIdx.x;
-    int fetched = 0;
-    if (tid == 0) fetched = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
-    int n = 0;
-    const float4* gp = p4 + tid;
-    if (cur < a.n_scans) {
-        const long long o0 = a.offsets[cur];
-        gp += o0 - a.origin;
-        n = (int)(a.offsets[cur + 1] - o0);
-    }
-#pragma unroll
-    for (int d = 0; d < D - 1; ++d) {
-#pragma unroll
-        for (int u = 0; u < kCpPts; ++u) {
-            const int i = d * SP + u * NT;
-            if (i + tid < n) cp_async16(ring_t + d * SLOT + u * (NT * 16), gp + i);
-        }
-        cp_async_commit();
-    }
-    for (int k = 0;; ++k) {
+    for (int k = 0; cur < a.n_scans; ++k) {
         const int b = k & 1;
-        if (tid == 0) mail[b ^ 1] = fetched;              // scan k + 1
-        bar_sync_all(kBarEmpty + b);                       // image b is free (and mail is visible)
-        if (cur >= a.n_scans) {
-            if (tid == 0) mail[2 + b] = -1;
-            bar_arrive_all(kBarFull + b);                  // tells the tail group to stop
-            bar_sync_all(kBarEmpty + (b ^ 1));             // consume its last arrival
-            break;
+        if (tid == 0) {                                   // publish scan k + 2, fetch scan k + 3
+            mail_write(mail, k + 2, pending);
+            pending = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
         }
-        const int nxt = mail[b ^ 1];
-        if (tid == 0) fetched = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);   // scan k + 2
+        const int nxt = mail_read(mail, k + 1);
         int nn = 0;
         const float4* gpn = p4 + tid;
         if (nxt < a.n_scans) {
@@ -576,9 +582,10 @@ __device__ __forceinline__ void ws_stream_role(const EncodeArgs& a, const Device
             gpn += o0 - a.origin;
             nn = (int)(a.offsets[nxt + 1] - o0);
         }
-        ws_stream_scan<ROWMODE>(gp, n, gpn, nn, ring_t, b ? img_b1 : img_b0, dp);
-        if (tid == 0) mail[2 + b] = cur;
-        bar_arrive_all(kBarFull + b);
+        if (k >= 2) mbar_wait(bars + 16 + 8 * b, ((k >> 1) - 1) & 1);     // image b is free again
+        ws_stream_scan<ROWMODE>(gp, n, gpn, nn, ring_t, b ? img_b1 : img_b0, dp, pol);
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(bars + 8 * b);
         cur = nxt;
         gp = gpn;
         n = nn;
@@ -590,7 +597,8 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
                                              unsigned char* smem, const WsLayout& L) {
     using G = TailGroup;
     const int gt = G::tid();
-    volatile int* mail = reinterpret_cast<volatile int*>(smem + L.mail_off);
+    const volatile long long* mail = reinterpret_cast<const volatile long long*>(smem + L.mail_off);
+    const uint32_t bars = smem_u32(smem + L.mbar_off);
     TailSmem S;
     S.tw = (float2*)(smem + L.tw_off);
     S.fa = (float2*)(smem + L.fa_off);
@@ -601,21 +609,24 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
     S.red = (double*)(smem + L.red_off);
     S.bin_start = smem + L.bins_off;
     const int D = dp.T * dp.n_bins;
-    bar_arrive_all(kBarEmpty + 0);
-    bar_arrive_all(kBarEmpty + 1);
     for (int k = 0;; ++k) {
         const int b = k & 1;
-        bar_sync_all(kBarFull + b);
-        const int scan = mail[2 + b];
-        if (scan < 0) break;
+        const int scan = mail_read(mail, k);
+        if (scan >= a.n_scans) break;
+        mbar_wait(bars + 8 * b, (k >> 1) & 1);            // every stream warp is done with image b
         S.img = (float*)(smem + (b ? L.img_off[1] : L.img_off[0]));
         S.fb = (float2*)S.img;
         uint32_t* img = reinterpret_cast<uint32_t*>(S.img);
         // the image is dead once the magnitudes are out of it: hand it back to the stream warps
         auto release = [&]() {
             for (int i = gt; i < L.img_words; i += G::kSize) img[i] = kInfBits;
-            bar_arrive_all(kBarEmpty + b);
+            __syncwarp();
+            if ((gt & 31) == 0) mbar_arrive(bars + 16 + 8 * b);
         };
+#ifdef NSC_EXP_SKIP_TAIL
+        release();      // measurement-only build: no tail at all (descriptors are not written)
+        continue;
+#endif
         float* stage0 = (a.img_out && a.stage == NSC_STAGE_PROJECTED)
                             ? a.img_out + (long long)scan * dp.E * kAz : nullptr;
         rows_to_filled<true, G>(S, dp.E, dp.interpolate != 0, stage0, [&dp](uint32_t key) {
@@ -631,8 +642,7 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
             spectrum_and_bins(S, dp, dp.E, [&](int p) { if (p == 9) release(); }, G());
             normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
                                 a.peers.row0 + scan, G());
-            // S.red / S.hist / S.src are next written after the kBarFull wait above, which every
-            // thread of this group has to reach first
+            G::sync();     // S.red / S.hist / S.src are rewritten by the next scan's tail
         } else {
             G::sync();     // every thread is done reading the image
             release();
@@ -644,7 +654,48 @@ template <int ROWMODE>
 __global__ void __launch_bounds__(kWsThreads, 1)
 encode_points_ws_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
     const WsLayout L(dp.E, dp.T, dp.n_bins);
+    const int tid = threadIdx.x;
+    const bool streamer = tid < kWsStreamThreads;
+    // The stream warps put the first stages of the CTA's first scan (its block index) in flight
+    // before anything else, so the tables below are built under the latency of those loads.
+    const float4* gp = reinterpret_cast<const float4*>(a.points) + tid;
+    int n = 0, pending = 0;
+    uint64_t pol = 0;
+    if (streamer) {
+#ifdef NSC_CP_EVICT_FIRST
+        pol = l2_evict_first_policy();
+#endif
+        const long long o0 = a.offsets[blockIdx.x];
+        gp += o0 - a.origin;
+        n = (int)(a.offsets[blockIdx.x + 1] - o0);
+        const uint32_t ring_t = smem_u32(smem_raw + L.ring_off) + tid * 16;
+#pragma unroll
+        for (int d = 0; d < D - 1; ++d) {
+#pragma unroll
+            for (int u = 0; u < kCpPts; ++u) {
+                const int i = d * SP + u * NT;
+                if (i + tid < n) cp_async16_hint(ring_t + d * SLOT + u * (NT * 16), gp + i, pol);
+            }
+            cp_async_commit();
+        }
+    }
+    if (tid == 0) {
+        volatile long long* mail = reinterpret_cast<volatile long long*>(smem_raw + L.mail_off);
+        const uint32_t bars = smem_u32(smem_raw + L.mbar_off);
+        mbar_init(bars, kWsStreamWarps);
+        mbar_init(bars + 8, kWsStreamWarps);
+        mbar_init(bars + 16, kWsTailWarps);
+        mbar_init(bars + 24, kWsTailWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int s1 = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
+        pending = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);      // scan 2, published in the loop
+        mail_write(mail, 0, (int)blockIdx.x);
+        mail_write(mail, 1, s1);
+        mail[2] = -1;                                                   // sequences that match no k
+        mail[3] = -1;
+    }
     {
         TailSmem S;
         S.tw = (float2*)(smem_raw + L.tw_off);
@@ -652,13 +703,13 @@ encode_points_ws_kernel(const __grid_constant__ EncodeArgs a, const __grid_const
         init_tail_tables(S, dp);
         uint32_t* i0 = reinterpret_cast<uint32_t*>(smem_raw + L.img_off[0]);
         uint32_t* i1 = reinterpret_cast<uint32_t*>(smem_raw + L.img_off[1]);
-        for (int i = threadIdx.x; i < L.img_words; i += kWsThreads) {
+        for (int i = tid; i < L.img_words; i += kWsThreads) {
             i0[i] = kInfBits;
             i1[i] = kInfBits;
         }
     }
     __syncthreads();
-    if (threadIdx.x < kWsStreamThreads) ws_stream_role<ROWMODE>(a, dp, smem_raw, L);
+    if (streamer) ws_stream_role<ROWMODE>(a, dp, smem_raw, L, gp, n, pending, pol);
     else ws_tail_role(a, dp, smem_raw, L);
 }
 

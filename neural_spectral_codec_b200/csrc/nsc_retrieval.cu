@@ -130,7 +130,8 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
         float c[kMaxPerLane];
         row_cdf<1>(ring, a.n_bins, PER, a.eps, lane, c);
 #pragma unroll
-        for (int i = 0; i < PER; ++i) qcdf[q * padded + lane * PER + i] = c[i];
+        for (int i = 0; i < PER; ++i)      // padding lanes hold 0, like the padding of the database rows
+            qcdf[q * padded + lane * PER + i] = lane * PER + i < a.n_bins ? c[i] : 0.0f;
         __syncwarp();
     }
     if (a.n_bins < padded)

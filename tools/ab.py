@@ -5,7 +5,8 @@ that drift of the box hits every spec alike, and prints scans/s, roofline fracti
     python tools/ab.py [--repeats 2] [--steps 30] [--tag r2a] [--args "--shape hdl32 --scans 4096"] SPEC...
 
 SPEC = label:variant[:ENV=VALUE,ENV=VALUE...]   variant "" = product library, otherwise
-libnsc_b200_<variant>.so (csrc/Makefile VARIANT=...). Example:
+libnsc_b200_<variant>.so (csrc/Makefile VARIANT=...). Labels starting with "x" are measurement-only
+builds (no valid descriptors): bench.py runs them with --no-checks. Example:
     tools/ab.py ws: old:tune:NSC_WS=0 d4:d4
 """
 import argparse
@@ -40,7 +41,7 @@ def main():
                     k, v = kv.split("=", 1)
                     env[k] = v
             cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.steps), "--warmup", "3",
-                   "--no-cpu", "--no-extras"] + a.args.split()
+                   "--no-cpu", "--no-extras"] + (["--no-checks"] if label.startswith("x") else []) + a.args.split()
             r = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=ROOT)
             if r.returncode != 0:
                 print(f"{label}: FAILED\n{r.stderr[-1500:]}", flush=True)
