@@ -33,7 +33,7 @@ int main(void) {
     st = nsc_pipeline_create(1 << 20, 2, 0, &pl);
     if (st != NSC_OK) { fprintf(stderr, "pipeline_create: %s %s\n", nsc_strerror(st), nsc_last_cuda_error()); return 1; }
     float* out = (float*)malloc(sizeof(float) * n_scans * prm.target_rows * prm.n_bins);
-    st = nsc_pipeline_encode(pl, pts, 4, offsets, n_scans, &prm, lut, out);
+    st = nsc_pipeline_encode(pl, pts, 4, offsets[n_scans], offsets, n_scans, &prm, lut, out);
     if (st != NSC_OK) { fprintf(stderr, "encode: %s %s\n", nsc_strerror(st), nsc_last_cuda_error()); return 1; }
     for (int s = 0; s < n_scans; ++s) {
         double sum = 0;

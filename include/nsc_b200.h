@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define NSC_ABI_VERSION 1
+#define NSC_ABI_VERSION 2
 #define NSC_N_AZIMUTH 360        /* the in-kernel FFT is a 360-point transform            */
 #define NSC_N_FREQS 181          /* n_azimuth/2 + 1, spectral_encoder.py:88               */
 #define NSC_MAX_ELEVATION 64     /* rows of the projected image held in shared memory     */
@@ -53,7 +53,7 @@ typedef enum nsc_status {
     NSC_ERR_BAD_LUT = -5,          /* freq->bin table not monotone / out of range          */
     NSC_ERR_WORKSPACE = -6,        /* workspace missing or too small                       */
     NSC_ERR_ALIGNMENT = -7,        /* stride-4 points must be 16-byte aligned              */
-    NSC_ERR_BAD_OFFSETS = -8,      /* host offsets not monotone                            */
+    NSC_ERR_BAD_OFFSETS = -8,      /* host offsets not monotone / outside the point buffer */
     NSC_ERR_CUDA = -9,             /* CUDA runtime error (see nsc_last_cuda_error)         */
     NSC_ERR_BAD_STRUCT = -10       /* struct_size does not match this ABI                  */
 } nsc_status;
@@ -120,11 +120,23 @@ int nsc_encode_batch(const float* d_points, int point_stride, const int64_t* d_o
  * db_row0 + i of EVERY database in h_peer_db[0..n_peers): host array of device pointers, one
  * per GPU of the box, peer-mapped into this process (CUDA IPC / symmetric memory), the local
  * database included. No separate collective pass; the caller synchronises all ranks
- * afterwards (a barrier), exactly as after an NCCL all-gather. */
+ * afterwards (nsc_peer_signal_wait below, or any barrier), exactly as after an NCCL all-gather. */
 int nsc_encode_batch_peers(const float* d_points, int point_stride, const int64_t* d_offsets,
                            int64_t point_origin, int n_scans, const nsc_params* p,
                            const int32_t* h_lut, float* const* h_peer_db, int n_peers,
                            int64_t db_row0, void* d_workspace, size_t workspace_bytes, void* stream);
+
+/* The synchronisation that ends a fused multi-GPU step, as ONE small kernel on `stream` (after
+ * the nsc_encode_batch_peers launch): tells every peer "rank `rank` has stored step `value`" by
+ * a system-scope release store into the peer's flag array, then spins with system-scope acquire
+ * loads until every peer has said the same to this rank. h_peer_flags[p]: device pointer
+ * (peer-mapped) to rank p's array of n_peers uint32 flags, zero before the first step; `value`
+ * must grow by one per step. With the step's database double-buffered by the caller (step s
+ * writes buffer s & 1) no barrier is needed BEFORE the encode: a rank that returns from the wait
+ * of step s-1 knows every peer has passed, in stream order, everything it enqueued before its own
+ * step s-1 -- including whatever read buffer s & 1 after step s-2. */
+int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, uint32_t value,
+                         void* stream);
 
 /* Replaces RangeImageProjector.project(points, keep_intensity=False)[0]
  * (stage = NSC_STAGE_PROJECTED) optionally followed by interpolate_range_image
@@ -167,10 +179,12 @@ void nsc_pipeline_destroy(nsc_pipeline* pl);
  * PCIe rate; pageable works), h_offsets int64[n_scans+1] starting at 0, h_out
  * float32[n_scans * target_rows * n_bins]. Chunks of whole scans are copied H2D, encoded
  * and copied back D2H on rotating streams so copies overlap compute. Synchronous: returns
- * when h_out is complete. A scan larger than max_chunk_points returns NSC_ERR_WORKSPACE. */
+ * when h_out is complete. A scan larger than max_chunk_points returns NSC_ERR_WORKSPACE;
+ * offsets that decrease, start below 0 or end beyond n_points (the length of h_points in
+ * points) return NSC_ERR_BAD_OFFSETS before anything is copied. */
 int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_stride,
-                        const int64_t* h_offsets, int n_scans, const nsc_params* p,
-                        const int32_t* h_lut, float* h_out);
+                        int64_t n_points, const int64_t* h_offsets, int n_scans,
+                        const nsc_params* p, const int32_t* h_lut, float* h_out);
 
 /* The same for scans that live in SEPARATE host arrays, as the reference's loaders hand them
  * out one np.fromfile() at a time (kitti_loader.py:100-115) -- the loop of pipeline.py:336-354

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NSC_LIB") or os.path.join(_HERE, "libnsc_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
-NSC_ABI_VERSION = 1
+NSC_ABI_VERSION = 2
 N_AZIMUTH = 360
 N_FREQS = 181
 MAX_ELEVATION = 64
@@ -66,13 +66,14 @@ SYMBOLS = {
     "nsc_workspace_bytes": (_SZ, [_I, _PP]),
     "nsc_encode_batch": (_I, [_VP, _I, _VP, _I64, _I, _PP, _VP, _VP, _VP, _SZ, _VP]),
     "nsc_encode_batch_peers": (_I, [_VP, _I, _VP, _I64, _I, _PP, _VP, _VP, _I, _I64, _VP, _SZ, _VP]),
+    "nsc_peer_signal_wait": (_I, [_VP, _I, _I, C.c_uint32, _VP]),
     "nsc_project_batch": (_I, [_VP, _I, _VP, _I64, _I, _PP, _I, _VP, _VP, _SZ, _VP]),
     "nsc_project_intensity_batch": (_I, [_VP, _VP, _I64, _I, _PP, _VP, _VP, _VP]),
     "nsc_encode_range_images": (_I, [_VP, _I, _I, _PP, _VP, _VP, _VP]),
     "nsc_interpolate_range_images": (_I, [_VP, _I, _I, _VP, _VP]),
     "nsc_pipeline_create": (_I, [_I64, _I, _I, C.POINTER(_VP)]),
     "nsc_pipeline_destroy": (None, [_VP]),
-    "nsc_pipeline_encode": (_I, [_VP, _VP, _I, _VP, _I, _PP, _VP, _VP]),
+    "nsc_pipeline_encode": (_I, [_VP, _VP, _I, _I64, _VP, _I, _PP, _VP, _VP]),
     "nsc_pipeline_encode_scans": (_I, [_VP, _VP, _VP, _I, _I, _PP, _VP, _VP]),
     "nsc_wasserstein_cdf": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_wasserstein_query": (_I, [_VP, _I, _VP, _I64, _I, C.c_float, _VP, _VP, C.c_double, _VP, _I,

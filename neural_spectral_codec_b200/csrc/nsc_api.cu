@@ -74,6 +74,40 @@ int nsc_encode_batch_peers(const float* d_points, int point_stride, const int64_
                          (unsigned*)d_workspace, (cudaStream_t)stream);
 }
 
+namespace {
+struct PeerFlags {
+    uint32_t* ptr[NSC_MAX_PEERS];
+};
+// Thread p: release-store `value` into peer p's flag of this rank, then acquire-poll this rank's
+// flag of peer p. Everything enqueued before this kernel on the stream (the encode kernel's peer
+// stores) is complete, and made visible system-wide by the fence, before any flag is raised.
+__global__ void peer_signal_wait_kernel(PeerFlags f, int n_peers, int rank, uint32_t value) {
+    const int p = threadIdx.x;
+    if (p >= n_peers) return;
+    __threadfence_system();
+    uint32_t* theirs = f.ptr[p] + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(value) : "memory");
+    const uint32_t* mine = f.ptr[rank] + p;
+    uint32_t seen;
+    do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+    } while ((int32_t)(seen - value) < 0);      // wrap-safe "seen < value"
+}
+}  // namespace
+
+int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, uint32_t value,
+                         void* stream) {
+    if (n_peers < 1 || n_peers > NSC_MAX_PEERS || rank < 0 || rank >= n_peers) return NSC_ERR_BAD_COUNT;
+    if (!h_peer_flags) return NSC_ERR_NULL_POINTER;
+    PeerFlags f;
+    for (int i = 0; i < NSC_MAX_PEERS; ++i) {
+        f.ptr[i] = i < n_peers ? h_peer_flags[i] : nullptr;
+        if (i < n_peers && !f.ptr[i]) return NSC_ERR_NULL_POINTER;
+    }
+    peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n_peers, rank, value);
+    return record_cuda(cudaGetLastError());
+}
+
 int nsc_project_batch(const float* d_points, int point_stride, const int64_t* d_offsets,
                       int64_t point_origin, int n_scans, const nsc_params* p, int stage,
                       float* d_images, void* d_workspace, size_t workspace_bytes, void* stream) {
@@ -196,8 +230,8 @@ int nsc_pipeline_create(int64_t max_chunk_points, int n_buffers, int device, nsc
 }
 
 int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_stride,
-                        const int64_t* h_offsets, int n_scans, const nsc_params* p,
-                        const int32_t* h_lut, float* h_out) {
+                        int64_t n_points, const int64_t* h_offsets, int n_scans,
+                        const nsc_params* p, const int32_t* h_lut, float* h_out) {
     if (!pl) return NSC_ERR_NULL_POINTER;
     DeviceParams dp;
     int st = make_device_params(p, h_lut, &dp);
@@ -206,6 +240,8 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
     if (point_stride != 3 && point_stride != 4) return NSC_ERR_BAD_STRIDE;
     if (n_scans == 0) return NSC_OK;
     if (!h_points || !h_offsets || !h_out) return NSC_ERR_NULL_POINTER;
+    if (n_points < 0) return NSC_ERR_BAD_COUNT;
+    if (h_offsets[0] < 0 || h_offsets[n_scans] > n_points) return NSC_ERR_BAD_OFFSETS;
     for (int i = 0; i < n_scans; ++i)
         if (h_offsets[i + 1] < h_offsets[i]) return NSC_ERR_BAD_OFFSETS;
     const int D = dp.T * dp.n_bins;

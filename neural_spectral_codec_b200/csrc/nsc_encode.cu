@@ -102,23 +102,6 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
-// Same with an L2 cache-policy operand (createpolicy evict_first: the points are read once).
-#ifdef NSC_CP_EVICT_FIRST
-__device__ __forceinline__ uint64_t l2_evict_first_policy() {
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-#endif
-__device__ __forceinline__ void cp_async16_hint(uint32_t dst, const void* src, uint64_t pol) {
-#ifdef NSC_CP_EVICT_FIRST
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol)
-                 : "memory");
-#else
-    (void)pol;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-#endif
-}
 __device__ __forceinline__ void cp_async_commit() {
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
@@ -418,27 +401,30 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
 }
 
 // ---- warp-specialised persistent kernel ---------------------------------------------------
-// One CTA per SM. kWsStreamWarps warps only stream points and scatter; kWsTailWarps warps only
-// run the tail (ranges, interpolation, FFT, bins, normalisation) of the scan the stream warps
-// finished before, from the other of two shared-memory images. The stream warps never wait for
-// a tail, and their cp.async ring keeps flowing across scan boundaries: the first stages of the
-// next scan are issued while the last stages of the current one are consumed (every scan is
-// padded to a multiple of kWsDepth stages so ring slots stay compile-time offsets).
-//
-// Hand-off through four mbarriers, so that no stream warp ever waits for another stream warp:
-//   full[b]   one arrival per stream warp when its share of the scan is in image b; the tail
-//             warps wait for the phase of scan k (parity (k >> 1) & 1)
-//   empty[b]  one arrival per tail warp when image b is re-initialised; a stream warp waits for
-//             it before its first scatter of scan k >= 2 (parity ((k >> 1) - 1) & 1)
-// Scan indices: the k-th scan of a CTA is its block index for k = 0 and comes from the work
-// counter afterwards, fetched by thread 0 two scans ahead and published in mail[k & 3] as
-// (sequence k, scan index); readers spin until the sequence matches (it practically always does).
-// An index >= n_scans ends both roles. kBarTail is the named barrier of the tail group alone.
+// One CTA of 1024 threads per SM, three roles:
+//   producer  (1 thread of the last warp) walks the CTA's scans and keeps kWsDepth whole stages
+//             of kWsStagePoints points in flight with cp.async.bulk (TMA, SASS UBLKCP), one copy
+//             per stage, straight across scan boundaries. Measured with no arithmetic at all
+//             (tools/feedbw.cu, profiles/r2c_feedbw.txt): 7.39 TB/s, against 6.93 TB/s for the
+//             per-thread cp.async ring and 7.28 TB/s for plain LDG.128.
+//   stream    (kWsStreamWarps warps) wait for a stage, read their points of it with LDS.128,
+//             classify and scatter into one of two shared-memory images, hand the slot back.
+//   tail      (kWsTailWarps warps) run ranges, interpolation, FFT, bins and normalisation of the
+//             scan the stream warps finished before, from the other image.
+// Synchronisation is by mbarriers only (plus the named barrier of the tail group):
+//   slot_full[s]   the producer's expect_tx + the copy's bytes            -> stream warps wait
+//   slot_empty[s]  one arrival per stream warp                            -> producer waits
+//   img_full[b]    one arrival per stream warp when scan k is in image b  -> tail warps wait
+//   img_empty[b]   one arrival per tail warp when image b is reset        -> stream warps wait
+// Scan indices: the producer takes the CTA's k-th scan (block index for k = 0, the work counter
+// afterwards) and publishes (k, scan, n_points) in mail[k & 3]; the other roles spin until the
+// sequence number matches. It reuses an entry only when the tail has finished scan k - 4
+// (tail_done), which every reader of that entry precedes. scan >= n_scans ends every role.
 #ifndef NSC_WS_STREAM_WARPS
 #define NSC_WS_STREAM_WARPS 24
 #endif
 #ifndef NSC_WS_TAIL_WARPS
-#define NSC_WS_TAIL_WARPS 8
+#define NSC_WS_TAIL_WARPS 7
 #endif
 #ifndef NSC_WS_DEPTH
 #define NSC_WS_DEPTH 5
@@ -447,11 +433,12 @@ constexpr int kWsStreamWarps = NSC_WS_STREAM_WARPS;
 constexpr int kWsTailWarps = NSC_WS_TAIL_WARPS;
 constexpr int kWsStreamThreads = kWsStreamWarps * 32;
 constexpr int kWsTailThreads = kWsTailWarps * 32;
-constexpr int kWsThreads = kWsStreamThreads + kWsTailThreads;
+constexpr int kWsThreads = kWsStreamThreads + kWsTailThreads + 32;     // + the producer's warp
 constexpr int kWsDepth = NSC_WS_DEPTH;
-constexpr int kWsStagePoints = kCpPts * kWsStreamThreads;
+constexpr int kWsPts = 2;                                              // points per stream thread per stage
+constexpr int kWsStagePoints = kWsPts * kWsStreamThreads;
 constexpr int kWsSlotBytes = kWsStagePoints * 16;
-constexpr int kBarTail = 1;
+constexpr int kBarTail = 1, kBarInit = 2;
 using TailGroup = ThreadGroup<kWsTailThreads, kBarTail, kWsStreamThreads>;
 static_assert(kWsThreads <= 1024 && kWsTailWarps <= kWarps, "warp split");
 
@@ -468,6 +455,7 @@ struct WsLayout {
         // an image doubles as the second FFT buffer of its own tail
         const int img_bytes = rows * kPitch * 4 > sig_bytes ? rows * kPitch * 4 : sig_bytes;
         img_words = rows * kPitch;
+        ring_off = take(kWsDepth * kWsSlotBytes);
         img_off[0] = take(img_bytes);
         img_off[1] = take(img_bytes);
         tw_off = take(kAz * 8);
@@ -478,127 +466,116 @@ struct WsLayout {
         src_off = take(rows * 4);
         red_off = take(kWarps * 8 + 16);
         bins_off = take(NSC_MAX_BINS + 3);
-        mail_off = take(4 * 8);
-        mbar_off = take(4 * 8);
-        ring_off = take(kWsDepth * kWsSlotBytes);
+        mail_off = take(4 * 16 + 16);                    // 4 entries + tail_done
+        mbar_off = take((2 * kWsDepth + 4) * 8);
         total = o;
     }
 };
 
-// mail entry: (sequence << 32) | scan index, one aligned 64-bit shared-memory word
-__device__ __forceinline__ void mail_write(volatile long long* mail, int k, int scan) {
-    mail[k & 3] = ((long long)k << 32) | (unsigned)scan;
-}
-__device__ __forceinline__ int mail_read(const volatile long long* mail, int k) {
-    long long v;
-    do v = mail[k & 3]; while ((int)(v >> 32) != k);
-    return (int)(unsigned)v;
+// mbarrier addresses behind L.mbar_off
+struct WsBars {
+    uint32_t base;
+    __device__ explicit WsBars(uint32_t b) : base(b) {}
+    __device__ uint32_t slot_full(uint32_t s) const { return base + 8 * s; }
+    __device__ uint32_t slot_empty(uint32_t s) const { return base + 8 * (kWsDepth + s); }
+    __device__ uint32_t img_full(int b) const { return base + 8 * (2 * kWsDepth + b); }
+    __device__ uint32_t img_empty(int b) const { return base + 8 * (2 * kWsDepth + 2 + b); }
+};
+
+// mail entry k & 3: int4 {sequence k, scan index, points of the scan, unused}
+__device__ __forceinline__ void mail_read(const volatile int* mail, int k, int& scan, int& n) {
+    const volatile int* e = mail + 4 * (k & 3);
+    while (e[0] != k) { }
+    __threadfence_block();
+    scan = e[1];
+    n = e[2];
 }
 
-// One scan of `n` points at gp (already offset by the thread index) through this thread's ring
-// into the image behind img_biased. Stages 0 .. kWsDepth-2 of the scan are in flight on entry;
-// on return the same holds for the next scan (gpn, nn).
-template <int ROWMODE>
-__device__ __forceinline__ void ws_stream_scan(const float4* __restrict__ gp, int n,
-                                               const float4* __restrict__ gpn, int nn,
-                                               uint32_t ring_t, uint32_t img_biased,
-                                               const DeviceParams& dp, uint64_t pol) {
-    constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
-    const int tid = threadIdx.x;
-    const int n_full = n / SP;
-    const int n_iter = (n + SP - 1) / SP;
-    int P = ((n_iter + D - 1) / D) * D;       // stages of this scan, padded (>= D: the loop below
-    if (P < D) P = D;                         // must issue the whole prologue of the next scan)
-    auto issue = [&](int j) {                 // stage j of this scan, or stage j - P of the next
-        const bool nx = j >= P;
-        const float4* base = nx ? gpn : gp;
-        const int m = nx ? nn : n;
-        const int jj = nx ? j - P : j;
-        const uint32_t dst = ring_t + (uint32_t)(j % D) * SLOT;
-#pragma unroll
-        for (int u = 0; u < kCpPts; ++u) {
-            const int i = jj * SP + u * NT;
-            if (i + tid < m) cp_async16_hint(dst + u * (NT * 16), base + i, pol);
+__device__ __forceinline__ void ws_producer_role(const EncodeArgs& a, unsigned char* smem, const WsLayout& L) {
+    volatile int* mail = reinterpret_cast<volatile int*>(smem + L.mail_off);
+    const volatile int* tail_done = mail + 16;
+    const WsBars bars(smem_u32(smem + L.mbar_off));
+    const uint32_t ring = smem_u32(smem + L.ring_off);
+    const float4* p4 = reinterpret_cast<const float4*>(a.points);
+    int scan = blockIdx.x;
+    int next = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
+    uint32_t slot = 0, phase = 0;                     // phase = (stage counter / kWsDepth) & 1
+    bool wrapped = false;
+    for (int k = 0;; ++k) {
+        int n = 0;
+        const float4* src = p4;
+        if (scan < a.n_scans) {
+            const long long o0 = a.offsets[scan];
+            n = (int)(a.offsets[scan + 1] - o0);
+            src += o0 - a.origin;
         }
-        cp_async_commit();
-    };
-    int it = 0;
-    for (; it + 2 * D - 2 < n_full; it += D) {          // every stage touched is full
-        const float4* g = gp + (long long)it * SP;
-#pragma unroll
-        for (int s = 0; s < D; ++s) {
-#pragma unroll
-            for (int u = 0; u < kCpPts; ++u)
-                cp_async16_hint(ring_t + ((s + D - 1) % D) * SLOT + u * (NT * 16),
-                                g + (s + D - 1) * SP + u * NT, pol);
-            cp_async_commit();
-            cp_async_wait<D - 1>();
-            float4 v[kCpPts];
-#pragma unroll
-            for (int u = 0; u < kCpPts; ++u) v[u] = lds128(ring_t + s * SLOT + u * (NT * 16));
-#pragma unroll
-            for (int u = 0; u < kCpPts; ++u)
-                project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+        while (*tail_done < k - 3) { }                // entry k & 3 is free: scan k - 4 is finished
+        volatile int* e = mail + 4 * (k & 3);
+        e[1] = scan;
+        e[2] = n;
+        __threadfence_block();
+        e[0] = k;
+        if (scan >= a.n_scans) break;
+        for (int base = 0; base < n; base += kWsStagePoints) {
+            if (wrapped) mbar_wait(bars.slot_empty(slot), phase ^ 1);
+            const uint32_t bytes = (uint32_t)min(kWsStagePoints, n - base) * 16u;
+            mbar_expect_tx(bars.slot_full(slot), bytes);
+            bulk_copy_g2s(ring + slot * kWsSlotBytes, src + base, bytes, bars.slot_full(slot));
+            if (++slot == kWsDepth) { slot = 0; phase ^= 1; wrapped = true; }
         }
-    }
-    for (; it < P; ++it) {
-        issue(it + D - 1);
-        cp_async_wait<D - 1>();
-        if (it < n_iter) {
-            const uint32_t src = ring_t + (uint32_t)(it % D) * SLOT;
-#pragma unroll
-            for (int u = 0; u < kCpPts; ++u) {
-                const int i = it * SP + u * NT + tid;
-                const float4 v = lds128(src + u * (NT * 16));
-                project_point<ROWMODE>(v.x, v.y, v.z, dp, img_biased, i < n);
-            }
-        }
+        scan = next;
+        if (scan < a.n_scans) next = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
     }
 }
 
 template <int ROWMODE>
 __device__ __forceinline__ void ws_stream_role(const EncodeArgs& a, const DeviceParams& dp,
-                                               unsigned char* smem, const WsLayout& L,
-                                               const float4* gp, int n, int pending, uint64_t pol) {
+                                               unsigned char* smem, const WsLayout& L) {
     const int tid = threadIdx.x;
+    const volatile int* mail = reinterpret_cast<const volatile int*>(smem + L.mail_off);
+    const WsBars bars(smem_u32(smem + L.mbar_off));
     const uint32_t ring_t = smem_u32(smem + L.ring_off) + tid * 16;
-    volatile long long* mail = reinterpret_cast<volatile long long*>(smem + L.mail_off);
-    const uint32_t bars = smem_u32(smem + L.mbar_off);     // full[0], full[1], empty[0], empty[1]
     const uint32_t bias = kFloorBias * (uint32_t)(kPitch * 4 + 4);
     const uint32_t img_b0 = smem_u32(smem + L.img_off[0]) - bias, img_b1 = smem_u32(smem + L.img_off[1]) - bias;
-    const float4* p4 = reinterpret_cast<const float4*>(a.points);
-    int cur = blockIdx.x;
-    for (int k = 0; cur < a.n_scans; ++k) {
+    uint32_t slot = 0, phase = 0;
+    for (int k = 0;; ++k) {
         const int b = k & 1;
-        if (tid == 0) {                                   // publish scan k + 2, fetch scan k + 3
-            mail_write(mail, k + 2, pending);
-            pending = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
+        int scan, n;
+        mail_read(mail, k, scan, n);
+        if (scan >= a.n_scans) break;
+        if (k >= 2) mbar_wait(bars.img_empty(b), ((k >> 1) - 1) & 1);      // image b is free again
+        const uint32_t img_biased = b ? img_b1 : img_b0;
+        for (int base = 0; base < n; base += kWsStagePoints) {
+            mbar_wait(bars.slot_full(slot), phase);
+            const uint32_t src = ring_t + slot * kWsSlotBytes;
+            float4 v[kWsPts];
+#pragma unroll
+            for (int u = 0; u < kWsPts; ++u) v[u] = lds128(src + u * (kWsStreamThreads * 16));
+            if (base + kWsStagePoints <= n) {
+#pragma unroll
+                for (int u = 0; u < kWsPts; ++u)
+                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+            } else {
+#pragma unroll
+                for (int u = 0; u < kWsPts; ++u)
+                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased,
+                                           base + u * kWsStreamThreads + tid < n);
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(bars.slot_empty(slot));
+            if (++slot == kWsDepth) { slot = 0; phase ^= 1; }
         }
-        const int nxt = mail_read(mail, k + 1);
-        int nn = 0;
-        const float4* gpn = p4 + tid;
-        if (nxt < a.n_scans) {
-            const long long o0 = a.offsets[nxt];
-            gpn += o0 - a.origin;
-            nn = (int)(a.offsets[nxt + 1] - o0);
-        }
-        if (k >= 2) mbar_wait(bars + 16 + 8 * b, ((k >> 1) - 1) & 1);     // image b is free again
-        ws_stream_scan<ROWMODE>(gp, n, gpn, nn, ring_t, b ? img_b1 : img_b0, dp, pol);
         __syncwarp();
-        if ((tid & 31) == 0) mbar_arrive(bars + 8 * b);
-        cur = nxt;
-        gp = gpn;
-        n = nn;
+        if ((tid & 31) == 0) mbar_arrive(bars.img_full(b));
     }
-    cp_async_wait<0>();
 }
 
 __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DeviceParams& dp,
                                              unsigned char* smem, const WsLayout& L) {
     using G = TailGroup;
     const int gt = G::tid();
-    const volatile long long* mail = reinterpret_cast<const volatile long long*>(smem + L.mail_off);
-    const uint32_t bars = smem_u32(smem + L.mbar_off);
+    volatile int* mail = reinterpret_cast<volatile int*>(smem + L.mail_off);
+    const WsBars bars(smem_u32(smem + L.mbar_off));
     TailSmem S;
     S.tw = (float2*)(smem + L.tw_off);
     S.fa = (float2*)(smem + L.fa_off);
@@ -608,12 +585,13 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
     S.src = (int*)(smem + L.src_off);
     S.red = (double*)(smem + L.red_off);
     S.bin_start = smem + L.bins_off;
-    const int D = dp.T * dp.n_bins;
+    [[maybe_unused]] const int D = dp.T * dp.n_bins;
     for (int k = 0;; ++k) {
         const int b = k & 1;
-        const int scan = mail_read(mail, k);
+        int scan, n_unused;
+        mail_read(mail, k, scan, n_unused);
         if (scan >= a.n_scans) break;
-        mbar_wait(bars + 8 * b, (k >> 1) & 1);            // every stream warp is done with image b
+        mbar_wait(bars.img_full(b), (k >> 1) & 1);        // every stream warp is done with image b
         S.img = (float*)(smem + (b ? L.img_off[1] : L.img_off[0]));
         S.fb = (float2*)S.img;
         uint32_t* img = reinterpret_cast<uint32_t*>(S.img);
@@ -621,12 +599,11 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
         auto release = [&]() {
             for (int i = gt; i < L.img_words; i += G::kSize) img[i] = kInfBits;
             __syncwarp();
-            if ((gt & 31) == 0) mbar_arrive(bars + 16 + 8 * b);
+            if ((gt & 31) == 0) mbar_arrive(bars.img_empty(b));
         };
 #ifdef NSC_EXP_SKIP_TAIL
         release();      // measurement-only build: no tail at all (descriptors are not written)
-        continue;
-#endif
+#else
         float* stage0 = (a.img_out && a.stage == NSC_STAGE_PROJECTED)
                             ? a.img_out + (long long)scan * dp.E * kAz : nullptr;
         rows_to_filled<true, G>(S, dp.E, dp.interpolate != 0, stage0, [&dp](uint32_t key) {
@@ -642,11 +619,13 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
             spectrum_and_bins(S, dp, dp.E, [&](int p) { if (p == 9) release(); }, G());
             normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
                                 a.peers.row0 + scan, G());
-            G::sync();     // S.red / S.hist / S.src are rewritten by the next scan's tail
         } else {
             G::sync();     // every thread is done reading the image
             release();
         }
+#endif
+        G::sync();         // S.red / S.hist / S.src are rewritten by the next scan's tail
+        if (gt == 0) mail[16] = k + 1;                    // tail_done
     }
 }
 
@@ -654,62 +633,49 @@ template <int ROWMODE>
 __global__ void __launch_bounds__(kWsThreads, 1)
 encode_points_ws_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant__ DeviceParams dp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr int D = kWsDepth, NT = kWsStreamThreads, SP = kWsStagePoints, SLOT = kWsSlotBytes;
     const WsLayout L(dp.E, dp.T, dp.n_bins);
     const int tid = threadIdx.x;
-    const bool streamer = tid < kWsStreamThreads;
-    // The stream warps put the first stages of the CTA's first scan (its block index) in flight
-    // before anything else, so the tables below are built under the latency of those loads.
-    const float4* gp = reinterpret_cast<const float4*>(a.points) + tid;
-    int n = 0, pending = 0;
-    uint64_t pol = 0;
-    if (streamer) {
-#ifdef NSC_CP_EVICT_FIRST
-        pol = l2_evict_first_policy();
-#endif
-        const long long o0 = a.offsets[blockIdx.x];
-        gp += o0 - a.origin;
-        n = (int)(a.offsets[blockIdx.x + 1] - o0);
-        const uint32_t ring_t = smem_u32(smem_raw + L.ring_off) + tid * 16;
-#pragma unroll
-        for (int d = 0; d < D - 1; ++d) {
-#pragma unroll
-            for (int u = 0; u < kCpPts; ++u) {
-                const int i = d * SP + u * NT;
-                if (i + tid < n) cp_async16_hint(ring_t + d * SLOT + u * (NT * 16), gp + i, pol);
-            }
-            cp_async_commit();
-        }
-    }
     if (tid == 0) {
-        volatile long long* mail = reinterpret_cast<volatile long long*>(smem_raw + L.mail_off);
-        const uint32_t bars = smem_u32(smem_raw + L.mbar_off);
-        mbar_init(bars, kWsStreamWarps);
-        mbar_init(bars + 8, kWsStreamWarps);
-        mbar_init(bars + 16, kWsTailWarps);
-        mbar_init(bars + 24, kWsTailWarps);
+        volatile int* mail = reinterpret_cast<volatile int*>(smem_raw + L.mail_off);
+        const WsBars bars(smem_u32(smem_raw + L.mbar_off));
+        for (int s = 0; s < kWsDepth; ++s) {
+            mbar_init(bars.slot_full(s), 1);
+            mbar_init(bars.slot_empty(s), kWsStreamWarps);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bars.img_full(b), kWsStreamWarps);
+            mbar_init(bars.img_empty(b), kWsTailWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int s1 = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
-        pending = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);      // scan 2, published in the loop
-        mail_write(mail, 0, (int)blockIdx.x);
-        mail_write(mail, 1, s1);
-        mail[2] = -1;                                                   // sequences that match no k
-        mail[3] = -1;
+        for (int i = 0; i < 4; ++i) mail[4 * i] = -1;      // sequence numbers that match no k
+        mail[16] = 0;                                       // tail_done
+    }
+    __syncthreads();
+    if (tid >= kWsStreamThreads + kWsTailThreads) {
+        // the producer starts copying at once; the tables below are built under its first loads
+        if (tid == kWsStreamThreads + kWsTailThreads) ws_producer_role(a, smem_raw, L);
+        return;
     }
     {
         TailSmem S;
         S.tw = (float2*)(smem_raw + L.tw_off);
         S.bin_start = smem_raw + L.bins_off;
-        init_tail_tables(S, dp);
+        constexpr int kWorkers = kWsStreamThreads + kWsTailThreads;
+        for (int m = tid; m < kAz; m += kWorkers) {
+            float sn, cs;
+            sincospif((float)m * (1.0f / 180.0f), &sn, &cs);
+            S.tw[m] = make_float2(cs, -sn);
+        }
+        for (int i = tid; i <= dp.n_bins; i += kWorkers) S.bin_start[i] = dp.bin_start[i];
         uint32_t* i0 = reinterpret_cast<uint32_t*>(smem_raw + L.img_off[0]);
         uint32_t* i1 = reinterpret_cast<uint32_t*>(smem_raw + L.img_off[1]);
-        for (int i = tid; i < L.img_words; i += kWsThreads) {
+        for (int i = tid; i < L.img_words; i += kWorkers) {
             i0[i] = kInfBits;
             i1[i] = kInfBits;
         }
+        asm volatile("bar.sync %0, %1;" ::"n"(kBarInit), "n"(kWorkers) : "memory");
     }
-    __syncthreads();
-    if (streamer) ws_stream_role<ROWMODE>(a, dp, smem_raw, L, gp, n, pending, pol);
+    if (tid < kWsStreamThreads) ws_stream_role<ROWMODE>(a, dp, smem_raw, L);
     else ws_tail_role(a, dp, smem_raw, L);
 }
 

@@ -7,8 +7,11 @@ One process per GPU (``torch.distributed``). Two ways to fill the database:
   * ``mode="nccl"``  -- fused encode kernel into a local block, then ONE
     ``all_gather_into_tensor`` over NVLink;
   * ``mode="fused"`` -- the database lives in symmetric memory and the encode kernel's epilogue
-    stores every descriptor straight into all peers' copies (``nsc_encode_batch_peers``); the
-    only collective left is the barrier that ends the step.
+    stores every descriptor straight into all peers' copies (``nsc_encode_batch_peers``). The
+    database is double-buffered (step s fills buffer s & 1), so nothing has to be synchronised
+    before the encode; the step ends with one small signal-and-wait kernel
+    (``nsc_peer_signal_wait``: a release store into every peer's flag array, acquire-polls on
+    this rank's own) instead of two symmetric-memory barriers.
 On the CPU test backend (gloo) the gather runs on host tensors produced elsewhere; the encode
 itself always needs a CUDA device.
 """
@@ -68,12 +71,23 @@ class ShardedEncoder:
             self._peer_ptrs = None
         else:
             import torch.distributed._symmetric_memory as symm
-            self.db = symm.empty((self.world * self.per, self.D), dtype=torch.float32, device=dev)
-            self.db.zero_()
             gname = (group or dist.group.WORLD).group_name
-            self._hdl = symm.rendezvous(self.db, gname)
-            ptrs = [int(self._hdl.buffer_ptrs[r]) for r in range(self.world)]
-            self._peer_ptrs = (C.c_void_p * self.world)(*ptrs)
+            rows = self.world * self.per
+            self._dbs = symm.empty((2, rows, self.D), dtype=torch.float32, device=dev)   # ping-pong
+            self._dbs.zero_()
+            self._hdl = symm.rendezvous(self._dbs, gname)
+            half = rows * self.D * 4
+            self._peer_ptrs = [(C.c_void_p * self.world)(*[int(self._hdl.buffer_ptrs[r]) + b * half
+                                                           for r in range(self.world)]) for b in (0, 1)]
+            self._flags = symm.empty((64,), dtype=torch.int32, device=dev)
+            self._flags.zero_()
+            self._flag_hdl = symm.rendezvous(self._flags, gname)
+            self._flag_ptrs = (C.c_void_p * self.world)(*[int(self._flag_hdl.buffer_ptrs[r])
+                                                          for r in range(self.world)])
+            self._flag_hdl.barrier()          # every rank's flags are zero before anyone signals
+            torch.cuda.synchronize(dev)
+            self._step = 0
+            self.db = self._dbs[0]
             self._ws = torch.empty(64, dtype=torch.int32, device=dev)
             self.local = None
 
@@ -92,18 +106,22 @@ class ShardedEncoder:
             lib = _lib.load()
             from .encoder import _check_batch
             points, offsets, n, stride = _check_batch(points, offsets)
-            # Peers store into this rank's database from THEIR streams: nobody may start writing
-            # pass k+1 before every rank's stream is past its reads of pass k.
-            self._hdl.barrier()
+            # Peers store into this rank's database from THEIR streams. Step s fills buffer s & 1:
+            # a rank that has left the wait of step s-1 knows every peer is past (in stream order)
+            # whatever read that buffer after step s-2, so the stores below need no barrier first.
+            b = self._step & 1
             p = self.encoder._params()
             lut = self.encoder.freq_to_bin()
+            stream = torch.cuda.current_stream(self.device).cuda_stream
             with torch.cuda.device(self.device):
                 st = lib.nsc_encode_batch_peers(
                     points.data_ptr(), stride, offsets.data_ptr(), 0, n, C.byref(p),
-                    lut.ctypes.data, self._peer_ptrs, self.world, self.rank * self.per,
-                    self._ws.data_ptr(), self._ws.numel() * 4,
-                    torch.cuda.current_stream(self.device).cuda_stream)
-            _lib.check(st, "nsc_encode_batch_peers")
-            self._hdl.barrier()
+                    lut.ctypes.data, self._peer_ptrs[b], self.world, self.rank * self.per,
+                    self._ws.data_ptr(), self._ws.numel() * 4, stream)
+                _lib.check(st, "nsc_encode_batch_peers")
+                self._step += 1
+                st = lib.nsc_peer_signal_wait(self._flag_ptrs, self.world, self.rank, self._step, stream)
+            _lib.check(st, "nsc_peer_signal_wait")
+            self.db = self._dbs[b]
         # rank r owns global rows [r*per, r*per + n_r): the database is contiguous in scan index
         return self.db[:self.n_scans]

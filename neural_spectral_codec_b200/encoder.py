@@ -135,6 +135,10 @@ def _check_batch(points: torch.Tensor, offsets: torch.Tensor):
     offsets = torch.as_tensor(offsets)
     if offsets.dim() != 1 or offsets.numel() < 1:
         raise ValueError("offsets must be a 1-D tensor of B+1 point offsets")
+    if not offsets.is_cuda:   # host offsets are cheap to validate; device offsets are the caller's contract
+        o = offsets.to(torch.int64)
+        if int(o[0]) < 0 or int(o[-1]) > points.shape[0] or bool((o[1:] < o[:-1]).any()):
+            raise ValueError("offsets must be non-decreasing, start at >= 0 and end at <= len(points)")
     offsets = offsets.to(device=points.device, dtype=torch.int64).contiguous()
     return points, offsets, offsets.numel() - 1, points.shape[1]
 
@@ -295,6 +299,9 @@ class SpectralEncoder(nn.Module):
                     or not pts.flags.c_contiguous:
                 raise ValueError("points must be contiguous float32 (sum N, 3|4)")
             offs = np.ascontiguousarray(offs, dtype=np.int64)
+            if offs.ndim != 1 or offs.shape[0] < 1 or offs[0] < 0 or offs[-1] > pts.shape[0] \
+                    or (np.diff(offs) < 0).any():
+                raise ValueError("offsets must be non-decreasing, start at >= 0 and end at <= len(points)")
         else:
             arrs = [_as_f32_points(s) for s in scans]
             widths = {a.shape[1] for a in arrs}
@@ -326,8 +333,8 @@ class SpectralEncoder(nn.Module):
                                                n_scans, C.byref(p), lut.ctypes.data, out.ctypes.data)
             _lib.check(st, "nsc_pipeline_encode_scans")
             return out
-        st = lib.nsc_pipeline_encode(self._pipeline, pts.ctypes.data, pts.shape[1], offs.ctypes.data,
-                                     n_scans, C.byref(p), lut.ctypes.data, out.ctypes.data)
+        st = lib.nsc_pipeline_encode(self._pipeline, pts.ctypes.data, pts.shape[1], pts.shape[0],
+                                     offs.ctypes.data, n_scans, C.byref(p), lut.ctypes.data, out.ctypes.data)
         _lib.check(st, "nsc_pipeline_encode")
         return out
 
@@ -351,6 +358,12 @@ class SpectralEncoder(nn.Module):
         dev = self._cuda_device("forward")
         if x.dim() != 3 or x.shape[2] != self.n_azimuth:
             raise ValueError("expected (batch, n_elevation, 360) range images")
+        if x.requires_grad and torch.is_grad_enabled():
+            # the reference's forward is differentiable w.r.t. the range image; this kernel is
+            # forward-only (no caller of the reference backpropagates through the encoder:
+            # gnn/trainer.py:115-119 optimises the GNN only, and every call site detaches)
+            raise RuntimeError("SpectralEncoder.forward is forward-only on this backend: call it under "
+                               "torch.no_grad() or pass range_images.detach()")
         x = x.detach().to(dev, torch.float32).contiguous()
         out = torch.empty((x.shape[0], self.output_dim), dtype=torch.float32, device=dev)
         p = self._params()

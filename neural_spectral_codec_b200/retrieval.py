@@ -116,9 +116,11 @@ class WassersteinRetriever:
         if n and q.shape[1] != self._hists.shape[1]:
             raise ValueError("query and database bin counts differ")
         k = min(int(top_k), n)
-        if k > MAX_TOP_K:
-            raise ValueError(f"top_k > {MAX_TOP_K}: take the distance matrix (return_distances=True) "
-                             "and select on the device")
+        # The select kernel holds its candidates in one CTA (k <= 1024). Larger k -- the reference's
+        # TwoStageRetrieval._global_retrieval asks for every keyframe, top_k = len(keyframes) -- takes
+        # the distance matrix of the same kernel and a stable device sort: the same (distance,
+        # lower index first) order.
+        k_kernel = k if k <= MAX_TOP_K else 0
         dist = torch.empty((nq, n), dtype=torch.float32, device=self.device)
         idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         top = torch.empty((nq, k), dtype=torch.float32, device=self.device)
@@ -132,10 +134,17 @@ class WassersteinRetriever:
                 st = lib.nsc_wasserstein_query(
                     q.data_ptr(), nq, self._cdfs.data_ptr(), n, q.shape[1], self.epsilon,
                     self._xyz.data_ptr() if use_xyz else None, qp.data_ptr() if use_xyz else None,
-                    float(spatial_filter_distance), dist.data_ptr(), k,
-                    idx.data_ptr() if k else None, top.data_ptr() if k else None,
-                    cnt.data_ptr() if k else None, torch.cuda.current_stream(self.device).cuda_stream)
+                    float(spatial_filter_distance), dist.data_ptr(), k_kernel,
+                    idx.data_ptr() if k_kernel else None, top.data_ptr() if k_kernel else None,
+                    cnt.data_ptr() if k_kernel else None, torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(st, "nsc_wasserstein_query")
+            if k > MAX_TOP_K:
+                sd, si = torch.sort(dist, dim=1, stable=True)
+                top, idx = sd[:, :k].contiguous(), si[:, :k].contiguous()
+                cnt = torch.isfinite(dist).sum(1).clamp(max=k).to(torch.int32)
+                beyond = torch.arange(k, device=self.device).unsqueeze(0) >= cnt.unsqueeze(1)
+                idx[beyond] = -1
+                top[beyond] = float("inf")
         if return_distances:
             return idx, top, cnt, dist
         return idx, top, cnt

@@ -375,6 +375,27 @@ def test_error_statuses_through_the_abi():
     bl[5] = 49
     assert call(l=bl) == -5
     torch.cuda.synchronize()
+    # host offsets are checked against the length of the host buffer before anything is copied
+    h = C.c_void_p()
+    assert lib.nsc_pipeline_create(1 << 16, 2, 0, C.byref(h)) == 0
+    hp = np.ones((16, 4), np.float32)
+    ho = np.zeros((1, 800), np.float32)
+    enc_call = lambda offs, n_points=16: lib.nsc_pipeline_encode(
+        h, hp.ctypes.data, 4, n_points, np.asarray(offs, np.int64).ctypes.data, 1, C.byref(p), lut.ctypes.data,
+        ho.ctypes.data)
+    assert enc_call([0, 16]) == 0
+    assert enc_call([0, 17]) == -8 and enc_call([-1, 16]) == -8 and enc_call([9, 3]) == -8
+    assert enc_call([0, 16], n_points=-1) == -3
+    lib.nsc_pipeline_destroy(h)
+    with pytest.raises(ValueError):
+        enc.encode_scans((hp, np.array([0, 17])))
+    with pytest.raises(ValueError):
+        enc.encode_points_batch(pts, torch.tensor([0, 17]))
+    x = torch.zeros(1, 16, 360, device="cuda", requires_grad=True)
+    with pytest.raises(RuntimeError):
+        enc(x)
+    with torch.no_grad():
+        assert enc(x).shape == (1, 800)
 
 
 def test_plain_c_caller_runs():

@@ -89,6 +89,49 @@ def test_random_database_against_oracle(n_db, n_q, k):
     assert torch.equal(again[0], idx) and torch.equal(again[1], top)       # deterministic
 
 
+@pytest.mark.parametrize("n_bins", [50, 100, 801, 7, 1024])
+def test_bin_counts_that_do_not_fill_the_lanes(n_bins):
+    """The reference's 50-bin histograms (and any n_bins that is not 32 x the kernel's per-lane
+    count): padding lanes must not add to the distance."""
+    rng = np.random.default_rng(n_bins)
+    db = rng.gamma(0.5, 1.0, (3000, n_bins)).astype(np.float32)
+    db /= db.sum(1, keepdims=True)
+    qs = db[[5, 77]] + (0.1 * rng.random((2, n_bins)) / n_bins).astype(np.float32)
+    r = retriever()
+    r.add_to_database(db)
+    idx, top, cnt, dist = r.query_batch(qs, top_k=10, return_distances=True)
+    for i in range(2):
+        ref = ro.wasserstein_distance_batch(torch.from_numpy(qs[i]), torch.from_numpy(db)).numpy()
+        np.testing.assert_allclose(dist[i].cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+        check_topk(idx[i].cpu().numpy(), top[i].cpu().numpy(), ref, 10)
+    from neural_spectral_codec_b200.retrieval import wasserstein_distance_batch
+    one = wasserstein_distance_batch(torch.from_numpy(qs[0]).cuda(), torch.from_numpy(db).cuda())
+    np.testing.assert_allclose(one.cpu().numpy(), ro.wasserstein_distance_batch(torch.from_numpy(qs[0]), torch.from_numpy(db)).numpy(),
+                               rtol=RTOL, atol=ATOL)
+
+
+def test_top_k_beyond_the_select_kernel_limit():
+    """TwoStageRetrieval._global_retrieval asks for every keyframe (top_k = len(keyframes),
+    two_stage_retrieval.py:182-185): more than 1024 of them must work like torch.topk does."""
+    rng = np.random.default_rng(4)
+    db = rng.gamma(0.5, 1.0, (2500, 800)).astype(np.float32)
+    db /= db.sum(1, keepdims=True)
+    xyz = np.stack([np.arange(len(db)) * 1.0, np.zeros(len(db)), np.zeros(len(db))], 1)
+    r = retriever()
+    r.add_to_database(db, positions=xyz)
+    q = db[40] * np.float32(2.0)
+    ref = ro.wasserstein_distance_batch(torch.from_numpy(q), torch.from_numpy(db)).numpy()
+    for k in (1500, 2500, 100000):
+        qi, qd = r.query(q, top_k=k)
+        kk = min(k, len(db))
+        assert qi.shape == (kk,) and qi.dtype == np.int64
+        check_topk(qi, qd, ref, kk)
+    idx, top, cnt = r.query_batch(q, top_k=2500, query_positions=xyz[40:41], spatial_filter_distance=100.0)
+    n_valid = int((np.abs(np.arange(len(db)) - 40) >= 100).sum())
+    assert cnt.item() == n_valid and (idx[0, n_valid:] == -1).all() and torch.isinf(top[0, n_valid:]).all()
+    assert (np.abs(idx[0, :n_valid].cpu().numpy() - 40) >= 100).all()
+
+
 def test_ties_break_by_lower_index_and_spatial_filter():
     rng = np.random.default_rng(1)
     base = rng.random((40, 800)).astype(np.float32)

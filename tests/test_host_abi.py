@@ -36,7 +36,7 @@ def test_every_declared_symbol_is_exported(lib):
     assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.nsc_abi_version() == 1
+    assert lib.nsc_abi_version() == _lib.NSC_ABI_VERSION == 2
     assert C.sizeof(_lib.NscParams) == default_params(lib).struct_size == 56
 
 
