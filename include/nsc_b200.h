@@ -195,6 +195,28 @@ int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, con
                               int point_stride, int n_scans, const nsc_params* p,
                               const int32_t* h_lut, float* h_out);
 
+/* ---- keyframe gate geometry (third "next" row) ------------------------------ */
+/* Voxel-set IoU of n_pairs cloud pairs in one launch: the geometric-novelty criterion of the
+ * reference's keyframe gate, compute_overlap (reference src/data/pose_utils.py:323-389) as called
+ * by KeyframeSelectionCriteria.check_geometric_novelty (src/keyframe/criteria.py:96-131), AFTER
+ * its random subsample (the caller draws it; the host mirror does so with the reference's NumPy
+ * calls, so equal seeds give equal results).
+ *   d_points   all clouds concatenated, float32 or float64 (points_are_f64), point_stride 3 | 4;
+ *              with stride 4 a non-finite 4th column drops the point, as in the reference
+ *   d_offsets  int64[2 * n_pairs + 1]: cloud A of pair i is points [off[2i], off[2i+1]), cloud B is
+ *              [off[2i+1], off[2i+2])
+ *   d_T        float64[n_pairs * 16], row-major 4x4 that maps A into B's frame (T_12)
+ *   d_counts   int32[n_pairs * 3]: voxels of A, voxels of B, voxels in both
+ *   d_iou      float64[n_pairs]: both / union, 0.0 for an empty union
+ * total_points = off[2 * n_pairs]; max_pair_points >= the largest |A| + |B| (pairs of up to
+ * 16384 points keep their hash set in shared memory). Workspace from
+ * nsc_voxel_overlap_workspace_bytes(total_points, max_pair_points, n_pairs). */
+size_t nsc_voxel_overlap_workspace_bytes(int64_t total_points, int64_t max_pair_points, int n_pairs);
+int nsc_voxel_overlap_batch(const void* d_points, int point_stride, int points_are_f64,
+                            const int64_t* d_offsets, int64_t total_points, int64_t max_pair_points,
+                            const double* d_T, int n_pairs, double voxel_size, int32_t* d_counts,
+                            double* d_iou, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* ---- stage-1 retrieval over the descriptor database (first "next" row) ---- */
 /* Normalised CDF rows of a block of database histograms: cdf = cumsum(h / (sum h + eps)) where
  * sum h > eps, cumsum(h) otherwise -- the database half of wasserstein_distance_batch_torch
@@ -217,12 +239,17 @@ int nsc_wasserstein_cdf(const float* d_hists, int64_t n_rows, int n_bins, float 
  *   top_k          0 = distances only; else <= 1024: d_top_idx int64[n_queries * top_k] (-1
  *                  padded), d_top_dist float32 (ascending, +inf padded), d_top_count
  *                  int32[n_queries] = min(top_k, rows not excluded). Ties are broken by the
- *                  lower database index (deterministic). */
+ *                  lower database index (deterministic).
+ *   d_workspace    nsc_wasserstein_workspace_bytes(n_queries) bytes, ZERO before the first call
+ *                  (every call leaves it zero where it matters). With it, top_k <= 128 is selected
+ *                  by many CTAs per query from per-warp minima kept by the distance pass; NULL or
+ *                  larger top_k: one CTA per query re-reads the distances. Same result. */
+size_t nsc_wasserstein_workspace_bytes(int n_queries);
 int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float* d_db_cdfs,
                           int64_t n_db, int n_bins, float epsilon, const double* d_db_xyz,
                           const double* d_query_xyz, double min_spatial_distance,
                           float* d_distances, int top_k, int64_t* d_top_idx, float* d_top_dist,
-                          int32_t* d_top_count, void* stream);
+                          int32_t* d_top_count, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* ---- descriptor wire format (fourth "next" row) --------------------------- */
 /* Replaces HistogramQuantizer.quantize / dequantize (reference src/encoding/quantization.py

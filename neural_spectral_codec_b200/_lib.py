@@ -75,9 +75,12 @@ SYMBOLS = {
     "nsc_pipeline_destroy": (None, [_VP]),
     "nsc_pipeline_encode": (_I, [_VP, _VP, _I, _I64, _VP, _I, _PP, _VP, _VP]),
     "nsc_pipeline_encode_scans": (_I, [_VP, _VP, _VP, _I, _I, _PP, _VP, _VP]),
+    "nsc_voxel_overlap_workspace_bytes": (_SZ, [_I64, _I64, _I]),
+    "nsc_voxel_overlap_batch": (_I, [_VP, _I, _I, _VP, _I64, _I64, _VP, _I, C.c_double, _VP, _VP, _VP, _SZ, _VP]),
     "nsc_wasserstein_cdf": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
+    "nsc_wasserstein_workspace_bytes": (_SZ, [_I]),
     "nsc_wasserstein_query": (_I, [_VP, _I, _VP, _I64, _I, C.c_float, _VP, _VP, C.c_double, _VP, _I,
-                                   _VP, _VP, _VP, _VP]),
+                                   _VP, _VP, _VP, _VP, _SZ, _VP]),
     "nsc_quantize_histograms": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_dequantize_histograms": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_test_host_classify": (_I, [_VP, _I, _I64, _PP, _VP, _VP, _VP]),

@@ -163,6 +163,23 @@ __device__ __forceinline__ void project_point(float x, float y, float z, const D
 #endif
 }
 
+// Two points through the packed FP32 pipe (classify2, nsc_point.h); same bits as two project_point calls.
+template <int ROWMODE>
+__device__ __forceinline__ void project_pair(const float4& a, const float4& b, const DeviceParams& dp,
+                                             uint32_t img_biased, bool in_a = true, bool in_b = true) {
+#if defined(NSC_EXP_NO_COMPUTE) || defined(NSC_NO_PACKED)
+    project_point<ROWMODE>(a.x, a.y, a.z, dp, img_biased, in_a);
+    project_point<ROWMODE>(b.x, b.y, b.z, dp, img_biased, in_b);
+#else
+    uint32_t ka, ra, ca, kb, rb, cb;
+    classify2(a.x, a.y, a.z, b.x, b.y, b.z, dp, ROWMODE, ka, ra, ca, kb, rb, cb);
+    if (!in_a) ka = 0xffffffffu;
+    if (!in_b) kb = 0xffffffffu;
+    scatter_min(img_biased, ra, ca, ka);
+    scatter_min(img_biased, rb, cb, kb);
+#endif
+}
+
 // Point pass over points [beg, beg + n) of the concatenated buffer: every kept point lowers the
 // key of its pixel in the shared-memory min image. CTA-collective (no barrier inside).
 template <int STRIDE, int ROWMODE, int FEED>
@@ -426,8 +443,13 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
 #ifndef NSC_WS_TAIL_WARPS
 #define NSC_WS_TAIL_WARPS 7
 #endif
+// Stage = 3 points per stream thread (36 KB per bulk copy), 4 stages: 144 KB ring. Measured
+// (profiles/r2g_ab_*.txt): 3 x 4 beats 2 x 6 by 1 %, 4 x 3 by 0.4 %, 6 x 2 by 4 %; 1 x 12 loses 15 %.
 #ifndef NSC_WS_DEPTH
-#define NSC_WS_DEPTH 5
+#define NSC_WS_DEPTH 4
+#endif
+#ifndef NSC_WS_PTS
+#define NSC_WS_PTS 3
 #endif
 constexpr int kWsStreamWarps = NSC_WS_STREAM_WARPS;
 constexpr int kWsTailWarps = NSC_WS_TAIL_WARPS;
@@ -435,7 +457,7 @@ constexpr int kWsStreamThreads = kWsStreamWarps * 32;
 constexpr int kWsTailThreads = kWsTailWarps * 32;
 constexpr int kWsThreads = kWsStreamThreads + kWsTailThreads + 32;     // + the producer's warp
 constexpr int kWsDepth = NSC_WS_DEPTH;
-constexpr int kWsPts = 2;                                              // points per stream thread per stage
+constexpr int kWsPts = NSC_WS_PTS;                                     // points per stream thread per stage
 constexpr int kWsStagePoints = kWsPts * kWsStreamThreads;
 constexpr int kWsSlotBytes = kWsStagePoints * 16;
 constexpr int kBarTail = 1, kBarInit = 2;
@@ -553,13 +575,17 @@ __device__ __forceinline__ void ws_stream_role(const EncodeArgs& a, const Device
             for (int u = 0; u < kWsPts; ++u) v[u] = lds128(src + u * (kWsStreamThreads * 16));
             if (base + kWsStagePoints <= n) {
 #pragma unroll
-                for (int u = 0; u < kWsPts; ++u)
-                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased);
+                for (int u = 0; u + 1 < kWsPts; u += 2) project_pair<ROWMODE>(v[u], v[u + 1], dp, img_biased);
+                if (kWsPts & 1)
+                    project_point<ROWMODE>(v[kWsPts - 1].x, v[kWsPts - 1].y, v[kWsPts - 1].z, dp, img_biased);
             } else {
 #pragma unroll
-                for (int u = 0; u < kWsPts; ++u)
-                    project_point<ROWMODE>(v[u].x, v[u].y, v[u].z, dp, img_biased,
-                                           base + u * kWsStreamThreads + tid < n);
+                for (int u = 0; u + 1 < kWsPts; u += 2)
+                    project_pair<ROWMODE>(v[u], v[u + 1], dp, img_biased, base + u * kWsStreamThreads + tid < n,
+                                          base + (u + 1) * kWsStreamThreads + tid < n);
+                if (kWsPts & 1)
+                    project_point<ROWMODE>(v[kWsPts - 1].x, v[kWsPts - 1].y, v[kWsPts - 1].z, dp, img_biased,
+                                           base + (kWsPts - 1) * kWsStreamThreads + tid < n);
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(bars.slot_empty(slot));
@@ -603,6 +629,55 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
         };
 #ifdef NSC_EXP_SKIP_TAIL
         release();      // measurement-only build: no tail at all (descriptors are not written)
+#elif defined(NSC_EXP_TAIL_PARTS)
+        // measurement-only builds: run only the parts of the tail selected by the bit mask
+        // (1 = ranges + interpolation, 2 = signal load + FFT, 4 = magnitudes + bins, 8 = normalise + store)
+        if (NSC_EXP_TAIL_PARTS & 1)
+            rows_to_filled<true, G>(S, dp.E, dp.interpolate != 0, nullptr, [&dp](uint32_t key) {
+                return key_is_empty(key, dp) ? 0.0f : __fsqrt_rn(__uint_as_float(key));
+            });
+        else if (gt < dp.E) S.src[gt] = gt;
+        G::sync();
+        {
+            const int n_sig = (dp.T + 1) / 2;
+            float* mag = reinterpret_cast<float*>(S.fa);
+            if (NSC_EXP_TAIL_PARTS & 2) {
+                for (int t = gt; t < n_sig * kAz; t += G::kSize) {
+                    const int g = t / kAz, n = t - g * kAz;
+                    S.fa[t] = make_float2(pooled_value(S, dp.E, dp.T, 2 * g, n), pooled_value(S, dp.E, dp.T, 2 * g + 1, n));
+                }
+                G::sync();
+                fft_pass<8, 1, G>(S.fa, S.fb, S.tw, n_sig);
+                G::sync();
+                fft_pass<9, 8, G>(S.fb, S.fa, S.tw, n_sig);
+                G::sync();
+                fft_pass<5, 72, G>(S.fa, S.fb, S.tw, n_sig);
+                G::sync();
+            }
+            if (NSC_EXP_TAIL_PARTS & 4) {
+                for (int t = gt; t < n_sig * kFreqs; t += G::kSize) {
+                    const int g = t / kFreqs, k = t - g * kFreqs;
+                    const float2* z = S.fb + g * kAz;
+                    const float2 p = z[k], m = z[k == 0 ? 0 : kAz - k];
+                    const float ar = p.x + m.x, ai = p.y - m.y, br = p.y + m.y, bi = p.x - m.x;
+                    mag[(2 * g) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(ar, ar, ai * ai));
+                    mag[(2 * g + 1) * kFreqs + k] = 0.5f * __fsqrt_rn(fmaf(br, br, bi * bi));
+                }
+                G::sync();
+            }
+            release();
+            if (NSC_EXP_TAIL_PARTS & 4) {
+                for (int i = gt; i < dp.T * dp.n_bins; i += G::kSize) {
+                    const int r = i / dp.n_bins, bb = i - r * dp.n_bins;
+                    float h = 0.0f;
+                    for (int k = S.bin_start[bb], k1 = S.bin_start[bb + 1]; k < k1; ++k) h += mag[r * kFreqs + k];
+                    S.hist[i] = h;
+                }
+            }
+            if (NSC_EXP_TAIL_PARTS & 8)
+                normalise_and_store(S, dp, a.out ? a.out + (long long)scan * D : nullptr, a.peers,
+                                    a.peers.row0 + scan, G());
+        }
 #else
         float* stage0 = (a.img_out && a.stage == NSC_STAGE_PROJECTED)
                             ? a.img_out + (long long)scan * dp.E * kAz : nullptr;

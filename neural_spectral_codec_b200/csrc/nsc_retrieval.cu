@@ -5,8 +5,15 @@
 //   cdf_rows_kernel        histogram rows -> normalised CDF rows, once per database insert
 //   wasserstein_kernel     streams the CDF rows once per group of <= kMaxQueries queries (HBM bound:
 //                          4*n_bins bytes per row), writes the (Q, N) distances, +inf where excluded
-//   topk_kernel            per query: 4-pass radix select of the k-th smallest distance, ordered
-//                          gather, bitonic sort of the k winners by (distance, index)
+//                          and every warp's smallest (distance, index) key per query
+//   select_kernel          k <= 128: many CTAs per query. The k-th smallest of 256 group minima
+//                          (groups of warp minima = disjoint row sets) bounds the k-th smallest key
+//                          from above; each CTA collects the keys of its slice under the bound (a
+//                          few more than k in all), the last CTA of a query sorts them. ~5 us
+//                          instead of one CTA re-reading all N distances.
+//   topk_kernel            larger k, or a candidate overflow of select_kernel (massive ties): one
+//                          CTA per query, per-thread-minimum bound + candidate sort, 4-pass radix
+//                          select as the last resort
 #include <math.h>
 
 #include "nsc_internal.h"
@@ -98,6 +105,7 @@ struct QueryArgs {
     const double* query_xyz;  // Q x 3 or null
     double min_dist;
     float* distances;         // Q x N
+    unsigned long long* warp_min;   // Q x (gridDim.x * kRWarps) smallest (distance bits, row) per warp, or null
     long long n_db;
     int n_queries, n_bins;
     float eps;
@@ -158,6 +166,9 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
     for (int s = 0; s < kRowStages - 1; ++s) issue(r0 + s * n_warps, s);
     const bool spatial = a.db_xyz != nullptr && a.query_xyz != nullptr;
     int slot = 0;
+    unsigned long long best[kMaxQueries];       // lane 0: smallest key of this warp's rows, per query
+#pragma unroll
+    for (int q = 0; q < kMaxQueries; ++q) best[q] = ~0ull;
     for (long long r = r0; r < a.n_db; r += n_warps) {
         issue(r + (kRowStages - 1) * n_warps, (slot + kRowStages - 1) % kRowStages);
         asm volatile("cp.async.wait_group %0;" ::"n"(kRowStages - 1) : "memory");
@@ -168,7 +179,9 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
         for (int i = 0; i < PER; ++i) c[i] = row_s[i];
         double px = 0, py = 0, pz = 0;
         if (spatial && lane == 0) { px = a.db_xyz[3 * r]; py = a.db_xyz[3 * r + 1]; pz = a.db_xyz[3 * r + 2]; }
-        for (int q = 0; q < a.n_queries; ++q) {
+#pragma unroll
+        for (int q = 0; q < kMaxQueries; ++q) {
+            if (q >= a.n_queries) break;
             const float* qc = qcdf + q * padded + lane * PER;
             float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
@@ -185,12 +198,20 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
                     if (sqrt(dx * dx + dy * dy + dz * dz) < a.min_dist) d = INFINITY;
                 }
                 a.distances[(long long)q * a.n_db + r] = d;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)r;
+                best[q] = key < best[q] ? key : best[q];
             }
         }
         __syncwarp();
         slot = (slot + 1) % kRowStages;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (a.warp_min && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < kMaxQueries; ++q)
+            if (q < a.n_queries)
+                a.warp_min[(long long)q * n_warps + (long long)blockIdx.x * kRWarps + warp] = best[q];
+    }
 }
 
 // ---- top-K ----------------------------------------------------------------------------------
@@ -201,7 +222,116 @@ struct TopkArgs {
     long long* top_idx;       // Q x k, -1 padded
     float* top_dist;          // Q x k, +inf padded
     int* top_count;           // Q
+    int* only_if;             // null, or per-query flags: run only where set (and clear it)
 };
+
+// Workspace of the selection, per query: counters {candidates, CTAs done, overflow, pad}, then
+// kSelCap candidate keys, then the warp minima of the distance pass. Zero before the first call;
+// every call leaves the counters zero again.
+constexpr int kSelThreads = 256;
+constexpr int kSelCap = 1024;
+constexpr int kSelMaxK = 128;
+constexpr int kSelCtas = 64;          // CTAs per query
+struct SelectArgs {
+    const float* distances;
+    const unsigned long long* warp_min;   // Q x n_min
+    int n_min;
+    long long n_db;
+    int k;
+    int* counters;                        // Q x 4
+    unsigned long long* cand;             // Q x kSelCap
+    long long* top_idx;
+    float* top_dist;
+    int* top_count;
+};
+
+// ascending bitonic sort of n (power of two, <= 1024) 64-bit keys in shared memory
+template <int NT>
+__device__ __forceinline__ void bitonic_sort_keys(unsigned long long* sel, unsigned n) {
+    for (unsigned size = 2; size <= n; size <<= 1) {
+        for (unsigned stride = size >> 1; stride > 0; stride >>= 1) {
+            for (unsigned t = threadIdx.x; t < n; t += NT) {
+                const unsigned j = t ^ stride;
+                if (j > t) {
+                    const unsigned long long x = sel[t], y = sel[j];
+                    const bool up = (t & size) == 0;
+                    if ((x > y) == up) { sel[t] = y; sel[j] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_kernel(const __grid_constant__ SelectArgs a) {
+    __shared__ unsigned long long sel[kSelCap];
+    __shared__ int s_last, s_count, s_valid;
+    const int q = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
+    const unsigned kInf = 0x7f800000u;
+    // 1. bound: k-th smallest of 256 group minima (each group = the rows of some warps)
+    unsigned long long m = ~0ull;
+    for (int i = tid; i < a.n_min; i += kSelThreads) {
+        const unsigned long long v = a.warp_min[(long long)q * a.n_min + i];
+        m = v < m ? v : m;
+    }
+    sel[tid] = m;
+    __syncthreads();
+    bitonic_sort_keys<kSelThreads>(sel, kSelThreads);
+    unsigned long long bound = sel[a.k - 1];
+    const unsigned long long finite_max = ((unsigned long long)(kInf - 1u) << 32) | 0xffffffffull;
+    if (bound > finite_max) bound = finite_max;            // fewer than k finite minima: take every finite key
+    __syncthreads();
+    // 2. this CTA's slice of the row: keys under the bound go to the query's candidate list
+    const long long per = (a.n_db + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)g * per, hi = lo + per < a.n_db ? lo + per : a.n_db;
+    const unsigned* keys = reinterpret_cast<const unsigned*>(a.distances + (long long)q * a.n_db);
+    int* cnt = a.counters + 4 * q;
+    for (long long i = lo + tid; i < hi; i += kSelThreads) {
+        const unsigned long long key = ((unsigned long long)keys[i] << 32) | (unsigned)i;
+        if (key <= bound) {
+            const int pos = atomicAdd(&cnt[0], 1);
+            if (pos < kSelCap) a.cand[(long long)q * kSelCap + pos] = key;
+        }
+    }
+    // 3. the last CTA of the query sorts the candidates
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int ticket = atomicAdd(&cnt[1], 1);
+        s_last = ticket == (int)gridDim.x - 1;
+        s_valid = 0;
+        if (s_last) {
+            __threadfence();
+            s_count = atomicAdd(&cnt[0], 0);
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    const int n_cand = s_count;
+    if (tid == 0) { cnt[0] = 0; cnt[1] = 0; }              // leave the workspace clean for the next call
+    if (n_cand > kSelCap) {                                 // massive ties: the one-CTA kernel takes over
+        if (tid == 0) cnt[2] = 1;
+        return;
+    }
+    for (int i = tid; i < kSelCap; i += kSelThreads)
+        sel[i] = i < n_cand ? __ldcg(a.cand + (long long)q * kSelCap + i) : ~0ull;
+    __syncthreads();
+    unsigned n_sort = 32;
+    while ((int)n_sort < n_cand) n_sort <<= 1;
+    bitonic_sort_keys<kSelThreads>(sel, n_sort);
+    int valid = 0;                                          // finite candidates among the first k
+    for (int i = tid; i < a.k; i += kSelThreads) {
+        const bool ok = i < n_cand && (unsigned)(sel[i] >> 32) < kInf;
+        a.top_idx[(long long)q * a.k + i] = ok ? (long long)(unsigned)(sel[i] & 0xffffffffull) : -1;
+        a.top_dist[(long long)q * a.k + i] = ok ? __uint_as_float((unsigned)(sel[i] >> 32)) : INFINITY;
+        valid += ok;
+    }
+    valid = __reduce_add_sync(0xffffffffu, valid);
+    if ((tid & 31) == 0 && valid) atomicAdd(&s_valid, valid);
+    __syncthreads();
+    if (tid == 0) a.top_count[q] = s_valid;
+}
 
 __device__ __forceinline__ unsigned block_excl_scan(unsigned v, unsigned* warp_tot, unsigned* total) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -257,6 +387,11 @@ topk_kernel(const __grid_constant__ TopkArgs a) {
     __shared__ unsigned s_total, s_prefix, s_need, s_nvalid, s_eq_total, s_fill;
     __shared__ unsigned long long sel[kTopThreads];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    if (a.only_if) {                     // fallback launch after select_kernel: usually nothing to do
+        if (a.only_if[4 * q + 2] == 0) return;
+        __syncthreads();
+        if (tid == 0) a.only_if[4 * q + 2] = 0;
+    }
     const unsigned* keys = reinterpret_cast<const unsigned*>(a.distances + (long long)q * a.n_db);
     const unsigned kInf = 0x7f800000u;
     const long long n_round = (a.n_db + kTopThreads - 1) / kTopThreads * kTopThreads;
@@ -413,11 +548,19 @@ int nsc_wasserstein_cdf(const float* d_hists, int64_t n_rows, int n_bins, float 
     return record_cuda(cudaGetLastError());
 }
 
+constexpr int kMaxDistGrid = 1024;     // CTAs of the distance pass (bounds the warp-minima rows of the workspace)
+
+size_t nsc_wasserstein_workspace_bytes(int n_queries) {
+    if (n_queries < 0) return 0;
+    const size_t per_query = 16 + (size_t)kSelCap * 8 + (size_t)kMaxDistGrid * kRWarps * 8;
+    return (size_t)n_queries * per_query + 256;
+}
+
 int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float* d_db_cdfs,
                           int64_t n_db, int n_bins, float epsilon, const double* d_db_xyz,
                           const double* d_query_xyz, double min_spatial_distance,
                           float* d_distances, int top_k, int64_t* d_top_idx, float* d_top_dist,
-                          int32_t* d_top_count, void* stream) {
+                          int32_t* d_top_count, void* d_workspace, size_t workspace_bytes, void* stream) {
     if (n_queries < 0 || n_db < 0 || top_k < 0) return NSC_ERR_BAD_COUNT;
     if (n_bins < 1 || n_bins > 32 * kMaxPerLane || top_k > kTopThreads) return NSC_ERR_BAD_PARAMS;
     if (n_db >= (1ll << 32)) return NSC_ERR_BAD_COUNT;
@@ -426,11 +569,38 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
     if (n_db > 0 && !d_db_cdfs) return NSC_ERR_NULL_POINTER;
     if (top_k > 0 && (!d_top_idx || !d_top_dist || !d_top_count)) return NSC_ERR_NULL_POINTER;
     if ((d_db_xyz == nullptr) != (d_query_xyz == nullptr)) return NSC_ERR_NULL_POINTER;
+    // the many-CTA selection needs the workspace; without one (or for large k) one CTA per query selects
+    const bool fused_select = top_k > 0 && top_k <= kSelMaxK && n_db > 0 && d_workspace &&
+                              workspace_bytes >= nsc_wasserstein_workspace_bytes(n_queries);
+    int* counters = (int*)d_workspace;
+    unsigned long long* cand = (unsigned long long*)((char*)d_workspace + (((size_t)n_queries * 16 + 255) & ~(size_t)255));
+    unsigned long long* warp_min = cand + (size_t)n_queries * kSelCap;
     cudaStream_t s = (cudaStream_t)stream;
     int sms = 0;
     int st = sm_count(&sms);
     if (st != NSC_OK) return st;
+    int n_min = 0;
     if (n_db > 0) {
+        void (*kern)(const QueryArgs) = nullptr;
+        int per = (n_bins + 31) / 32;
+        if (per <= 8) { kern = wasserstein_kernel<8>; per = 8; }
+        else if (per <= 16) { kern = wasserstein_kernel<16>; per = 16; }
+        else if (per <= 25) { kern = wasserstein_kernel<25>; per = 25; }
+        else { kern = wasserstein_kernel<32>; per = 32; }
+        // one grid for every group of queries (sized for the largest group), so that the rows of
+        // warp minima have one length
+        const int q_max = n_queries < kMaxQueries ? n_queries : kMaxQueries;
+        const size_t smem_max = (size_t)(q_max + kRWarps * kRowStages) * per * 32 * 4;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        if (e != cudaSuccess) return record_cuda(e);
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRThreads, smem_max);
+        if (e != cudaSuccess) return record_cuda(e);
+        if (per_sm < 1) return NSC_ERR_BAD_PARAMS;
+        long long grid = (n_db + kRWarps - 1) / kRWarps;
+        if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
+        if (grid > kMaxDistGrid) grid = kMaxDistGrid;
+        n_min = (int)grid * kRWarps;
         for (int q0 = 0; q0 < n_queries; q0 += kMaxQueries) {
             QueryArgs a;
             a.n_queries = n_queries - q0 < kMaxQueries ? n_queries - q0 : kMaxQueries;
@@ -440,24 +610,11 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             a.query_xyz = d_query_xyz ? d_query_xyz + 3 * (size_t)q0 : nullptr;
             a.min_dist = min_spatial_distance;
             a.distances = d_distances + (size_t)q0 * n_db;
+            a.warp_min = fused_select ? warp_min + (size_t)q0 * n_min : nullptr;
             a.n_db = n_db;
             a.n_bins = n_bins;
             a.eps = epsilon;
-            void (*kern)(const QueryArgs) = nullptr;
-            int per = (n_bins + 31) / 32;
-            if (per <= 8) { kern = wasserstein_kernel<8>; per = 8; }
-            else if (per <= 16) { kern = wasserstein_kernel<16>; per = 16; }
-            else if (per <= 25) { kern = wasserstein_kernel<25>; per = 25; }
-            else { kern = wasserstein_kernel<32>; per = 32; }
             const size_t smem = (size_t)(a.n_queries + kRWarps * kRowStages) * per * 32 * 4;
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return record_cuda(e);
-            int per_sm = 0;
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRThreads, smem);
-            if (e != cudaSuccess) return record_cuda(e);
-            if (per_sm < 1) return NSC_ERR_BAD_PARAMS;
-            long long grid = (n_db + kRWarps - 1) / kRWarps;
-            if (grid > (long long)sms * per_sm) grid = (long long)sms * per_sm;
             kern<<<(int)grid, kRThreads, smem, s>>>(a);
             e = cudaGetLastError();
             if (e != cudaSuccess) return record_cuda(e);
@@ -471,6 +628,26 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
         t.top_idx = (long long*)d_top_idx;
         t.top_dist = d_top_dist;
         t.top_count = d_top_count;
+        t.only_if = nullptr;
+        if (fused_select) {
+            SelectArgs sa;
+            sa.distances = d_distances;
+            sa.warp_min = warp_min;
+            sa.n_min = n_min;
+            sa.n_db = n_db;
+            sa.k = top_k;
+            sa.counters = counters;
+            sa.cand = cand;
+            sa.top_idx = (long long*)d_top_idx;
+            sa.top_dist = d_top_dist;
+            sa.top_count = d_top_count;
+            long long per_q = (n_db + 4 * kSelThreads - 1) / (4 * kSelThreads);      // >= 1024 rows per CTA
+            const int ctas = (int)(per_q < 1 ? 1 : per_q > kSelCtas ? kSelCtas : per_q);
+            select_kernel<<<dim3(ctas, n_queries), kSelThreads, 0, s>>>(sa);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) return record_cuda(e);
+            t.only_if = counters;           // runs only for queries whose candidates overflowed
+        }
         topk_kernel<<<n_queries, kTopThreads, 0, s>>>(t);
         return record_cuda(cudaGetLastError());
     }

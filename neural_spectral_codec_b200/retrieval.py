@@ -36,6 +36,7 @@ class WassersteinRetriever:
         self._hists: Optional[torch.Tensor] = None      # capacity x n_bins
         self._cdfs: Optional[torch.Tensor] = None
         self._xyz: Optional[torch.Tensor] = None        # capacity x 3 float64 (NaN = unknown)
+        self._ws: Optional[torch.Tensor] = None         # selection workspace (zero between calls)
         self.database_size = 0
 
     # -- database ---------------------------------------------------------------------------
@@ -130,13 +131,17 @@ class WassersteinRetriever:
             qp = None
             if use_xyz:
                 qp = torch.as_tensor(query_positions, dtype=torch.float64).reshape(nq, 3).to(self.device).contiguous()
+            need = int(lib.nsc_wasserstein_workspace_bytes(nq))
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = torch.zeros(need, dtype=torch.uint8, device=self.device)
             with torch.cuda.device(self.device):
                 st = lib.nsc_wasserstein_query(
                     q.data_ptr(), nq, self._cdfs.data_ptr(), n, q.shape[1], self.epsilon,
                     self._xyz.data_ptr() if use_xyz else None, qp.data_ptr() if use_xyz else None,
                     float(spatial_filter_distance), dist.data_ptr(), k_kernel,
                     idx.data_ptr() if k_kernel else None, top.data_ptr() if k_kernel else None,
-                    cnt.data_ptr() if k_kernel else None, torch.cuda.current_stream(self.device).cuda_stream)
+                    cnt.data_ptr() if k_kernel else None, self._ws.data_ptr(), self._ws.numel(),
+                    torch.cuda.current_stream(self.device).cuda_stream)
             _lib.check(st, "nsc_wasserstein_query")
             if k > MAX_TOP_K:
                 sd, si = torch.sort(dist, dim=1, stable=True)
