@@ -162,9 +162,13 @@ int nsc_project_intensity_batch(const float* d_points, const int64_t* d_offsets,
 int nsc_encode_range_images(const float* d_images, int n_images, int rows, const nsc_params* p,
                             const int32_t* h_lut, float* d_out, void* stream);
 
-/* Replaces interpolate_range_image(img, 'linear') (range_image.py:15-89) on a batch of
- * images already on the device. In and out may alias. */
-int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows,
+/* Replaces interpolate_range_image(img, method) (range_image.py:15-89) on a batch of images
+ * already on the device: method NSC_INTERP_LINEAR = circular linear interpolation along azimuth
+ * (the encoder's path), NSC_INTERP_NEAREST = nearest valid pixel (:66-75, the lower column on a
+ * tie); both followed by the empty-row fill (:77-87). In and out may alias. */
+#define NSC_INTERP_LINEAR 0
+#define NSC_INTERP_NEAREST 1
+int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows, int method,
                                  float* d_images_out, void* stream);
 
 /* ---- host-buffer pipeline (the end-to-end call: H2D, encode, D2H inside) -------------- */

@@ -140,13 +140,15 @@ int nsc_encode_range_images(const float* d_images, int n_images, int rows, const
     return launch_encode_images(d_images, n_images, rows, dp, d_out, (cudaStream_t)stream);
 }
 
-int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows,
+int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows, int method,
                                  float* d_images_out, void* stream) {
     if (n_images < 0) return NSC_ERR_BAD_COUNT;
     if (rows < 1 || rows > NSC_MAX_ELEVATION) return NSC_ERR_BAD_PARAMS;
+    if (method != NSC_INTERP_LINEAR && method != NSC_INTERP_NEAREST) return NSC_ERR_BAD_PARAMS;
     if (n_images == 0) return NSC_OK;
     if (!d_images_in || !d_images_out) return NSC_ERR_NULL_POINTER;
-    return launch_interpolate(d_images_in, n_images, rows, d_images_out, (cudaStream_t)stream);
+    return launch_interpolate(d_images_in, n_images, rows, method == NSC_INTERP_NEAREST, d_images_out,
+                              (cudaStream_t)stream);
 }
 
 /* ---- host-buffer pipeline ------------------------------------------------------------- */

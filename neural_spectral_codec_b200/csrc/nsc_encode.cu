@@ -829,7 +829,7 @@ encode_images_kernel(const float* __restrict__ images, int n_images, int rows,
 
 // interpolate_range_image on device images (range_image.py:15-89).
 __global__ void __launch_bounds__(kThreads, kMinBlocks)
-interpolate_kernel(const float* __restrict__ in, int n_images, int rows, float* __restrict__ out) {
+interpolate_kernel(const float* __restrict__ in, int n_images, int rows, int nearest, float* __restrict__ out) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const SmemLayout L(rows, 1, 1);
     const TailSmem S(smem_raw, L);
@@ -841,7 +841,7 @@ interpolate_kernel(const float* __restrict__ in, int n_images, int rows, float* 
             S.img[r * kPitch + c] = src[i];
         }
         __syncthreads();
-        rows_to_filled<false>(S, rows, true, nullptr, [](uint32_t) { return 0.0f; });
+        rows_to_filled<false>(S, rows, true, nullptr, [](uint32_t) { return 0.0f; }, nearest != 0);
         float* dst = out + (long long)im * rows * kAz;
         for (int i = threadIdx.x; i < rows * kAz; i += kThreads) {
             const int r = i / kAz, c = i - r * kAz;
@@ -1057,7 +1057,7 @@ int launch_encode_images(const float* d_images, int n_images, int rows, const De
     return record_cuda(cudaGetLastError());
 }
 
-int launch_interpolate(const float* d_in, int n_images, int rows, float* d_out, cudaStream_t stream) {
+int launch_interpolate(const float* d_in, int n_images, int rows, int nearest, float* d_out, cudaStream_t stream) {
     if (n_images == 0) return NSC_OK;
     DeviceInfo di;
     int st = device_info(&di);
@@ -1068,7 +1068,7 @@ int launch_interpolate(const float* d_in, int n_images, int rows, float* d_out, 
     if (st != NSC_OK) return st;
     int grid = di.sms * per_sm;
     if (grid > n_images) grid = n_images;
-    interpolate_kernel<<<grid, kThreads, L.total, stream>>>(d_in, n_images, rows, d_out);
+    interpolate_kernel<<<grid, kThreads, L.total, stream>>>(d_in, n_images, rows, nearest, d_out);
     return record_cuda(cudaGetLastError());
 }
 

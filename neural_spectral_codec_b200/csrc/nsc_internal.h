@@ -50,7 +50,7 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
                   unsigned* d_workspace, cudaStream_t stream);
 int launch_encode_images(const float* d_images, int n_images, int rows, const DeviceParams& dp,
                          float* d_out, cudaStream_t stream);
-int launch_interpolate(const float* d_in, int n_images, int rows, float* d_out, cudaStream_t stream);
+int launch_interpolate(const float* d_in, int n_images, int rows, int nearest, float* d_out, cudaStream_t stream);
 size_t workspace_bytes_for(int n_scans, int E);
 
 }  // namespace nsc

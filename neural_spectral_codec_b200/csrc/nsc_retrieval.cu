@@ -231,7 +231,7 @@ struct TopkArgs {
 constexpr int kSelThreads = 256;
 constexpr int kSelCap = 1024;
 constexpr int kSelMaxK = 128;
-constexpr int kSelCtas = 64;          // CTAs per query
+constexpr int kSelCtas = 128;         // CTAs per query, at most
 struct SelectArgs {
     const float* distances;
     const unsigned long long* warp_min;   // Q x n_min
@@ -271,9 +271,20 @@ select_kernel(const __grid_constant__ SelectArgs a) {
     const unsigned kInf = 0x7f800000u;
     // 1. bound: k-th smallest of 256 group minima (each group = the rows of some warps)
     unsigned long long m = ~0ull;
-    for (int i = tid; i < a.n_min; i += kSelThreads) {
-        const unsigned long long v = a.warp_min[(long long)q * a.n_min + i];
-        m = v < m ? v : m;
+    {
+        const unsigned long long* wm = a.warp_min + (long long)q * a.n_min;
+        int i = tid;
+        for (; i + 3 * kSelThreads < a.n_min; i += 4 * kSelThreads) {        // four loads in flight
+            const unsigned long long v0 = __ldcg(wm + i), v1 = __ldcg(wm + i + kSelThreads),
+                                     v2 = __ldcg(wm + i + 2 * kSelThreads), v3 = __ldcg(wm + i + 3 * kSelThreads);
+            const unsigned long long a01 = v0 < v1 ? v0 : v1, a23 = v2 < v3 ? v2 : v3;
+            const unsigned long long a03 = a01 < a23 ? a01 : a23;
+            m = a03 < m ? a03 : m;
+        }
+        for (; i < a.n_min; i += kSelThreads) {
+            const unsigned long long v = __ldcg(wm + i);
+            m = v < m ? v : m;
+        }
     }
     sel[tid] = m;
     __syncthreads();
@@ -287,12 +298,24 @@ select_kernel(const __grid_constant__ SelectArgs a) {
     const long long lo = (long long)g * per, hi = lo + per < a.n_db ? lo + per : a.n_db;
     const unsigned* keys = reinterpret_cast<const unsigned*>(a.distances + (long long)q * a.n_db);
     int* cnt = a.counters + 4 * q;
-    for (long long i = lo + tid; i < hi; i += kSelThreads) {
-        const unsigned long long key = ((unsigned long long)keys[i] << 32) | (unsigned)i;
+    auto consider = [&](unsigned bits, long long i) {
+        const unsigned long long key = ((unsigned long long)bits << 32) | (unsigned)i;
         if (key <= bound) {
             const int pos = atomicAdd(&cnt[0], 1);
             if (pos < kSelCap) a.cand[(long long)q * kSelCap + pos] = key;
         }
+    };
+    {
+        long long i = lo + tid;
+        for (; i + 3 * kSelThreads < hi; i += 4 * kSelThreads) {               // four loads in flight
+            const unsigned k0 = __ldcg(keys + i), k1 = __ldcg(keys + i + kSelThreads),
+                           k2 = __ldcg(keys + i + 2 * kSelThreads), k3 = __ldcg(keys + i + 3 * kSelThreads);
+            consider(k0, i);
+            consider(k1, i + kSelThreads);
+            consider(k2, i + 2 * kSelThreads);
+            consider(k3, i + 3 * kSelThreads);
+        }
+        for (; i < hi; i += kSelThreads) consider(__ldcg(keys + i), i);
     }
     // 3. the last CTA of the query sorts the candidates
     __threadfence();
@@ -641,7 +664,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             sa.top_idx = (long long*)d_top_idx;
             sa.top_dist = d_top_dist;
             sa.top_count = d_top_count;
-            long long per_q = (n_db + 4 * kSelThreads - 1) / (4 * kSelThreads);      // >= 1024 rows per CTA
+            long long per_q = (n_db + 4 * kSelThreads - 1) / (4 * kSelThreads);      // ~1024 rows per CTA
             const int ctas = (int)(per_q < 1 ? 1 : per_q > kSelCtas ? kSelCtas : per_q);
             select_kernel<<<dim3(ctas, n_queries), kSelThreads, 0, s>>>(sa);
             cudaError_t e = cudaGetLastError();

@@ -136,9 +136,13 @@ __device__ __forceinline__ int next_valid(const uint32_t* m, int x) {
 // so no block barrier separates the three steps. FROM_KEYS: the row holds the bits of the min
 // of s per pixel (plus the 361st column for azimuth == 2 pi); `to_value(key)` maps them to ranges.
 // `stage0`, if not null, receives the un-interpolated rows (rows x 360, global memory).
+// `nearest` selects interpolate_range_image(method='nearest') (range_image.py:66-75): a hole takes
+// the value of the valid pixel at the smallest circular distance, the lower column on a tie
+// (np.argmin over ascending valid indices).
 template <bool FROM_KEYS, typename G = CtaGroup, typename ToValue>
 __device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool interpolate,
-                                               float* __restrict__ stage0, ToValue to_value) {
+                                               float* __restrict__ stage0, ToValue to_value,
+                                               bool nearest = false) {
     const int warp = G::tid() >> 5, lane = G::tid() & 31;
     for (int r = warp; r < rows; r += G::kGroupWarps) {
         float* row = S.img + r * kPitch;
@@ -170,8 +174,14 @@ __device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool
             for (int x = lane; x < kAz; x += 32) {
                 if ((m[x >> 5] >> (x & 31)) & 1u) continue;
                 const int xl = prev_valid(m, x), xr = next_valid(m, x);
-                const double fl = (double)row[xl < 0 ? xl + kAz : xl];
-                const double fr = (double)row[xr >= kAz ? xr - kAz : xr];
+                const int il = xl < 0 ? xl + kAz : xl, ir = xr >= kAz ? xr - kAz : xr;
+                if (nearest) {
+                    const int dl = x - xl, dr = xr - x;
+                    row[x] = row[dl < dr || (dl == dr && il < ir) ? il : ir];
+                    continue;
+                }
+                const double fl = (double)row[il];
+                const double fr = (double)row[ir];
                 // np.interp: slope = (fp[j+1]-fp[j])/(xp[j+1]-xp[j]); slope*(x-xp[j]) + fp[j], float64
                 const double slope = __ddiv_rn(__dsub_rn(fr, fl), (double)(xr - xl));
                 row[x] = __double2float_rn(__dadd_rn(__dmul_rn(slope, (double)(x - xl)), fl));

@@ -387,8 +387,9 @@ def interpolate_range_image(range_image: Union[np.ndarray, torch.Tensor], method
                             device="cuda"):
     """``interpolate_range_image`` of the reference (range_image.py:15-89) on the GPU. Accepts a
     ``(rows, 360)`` image or a ``(B, rows, 360)`` batch; numpy in -> numpy out."""
-    if method != "linear":
-        raise ValueError("only the 'linear' method is on the encoding path")
+    if method not in ("linear", "nearest"):
+        # the reference silently leaves the holes of partly filled rows for any other string
+        raise ValueError("method must be 'linear' or 'nearest'")
     lib = _lib.load()
     is_np = isinstance(range_image, np.ndarray)
     x = torch.from_numpy(np.ascontiguousarray(range_image, np.float32)) if is_np else range_image
@@ -400,7 +401,8 @@ def interpolate_range_image(range_image: Union[np.ndarray, torch.Tensor], method
     x = x.to(torch.float32).contiguous()
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
-        st = lib.nsc_interpolate_range_images(x.data_ptr(), x.shape[0], x.shape[1], out.data_ptr(),
+        st = lib.nsc_interpolate_range_images(x.data_ptr(), x.shape[0], x.shape[1],
+                                              1 if method == "nearest" else 0, out.data_ptr(),
                                               torch.cuda.current_stream(x.device).cuda_stream)
     _lib.check(st, "nsc_interpolate_range_images")
     if single:

@@ -125,7 +125,8 @@ class WassersteinRetriever:
         dist = torch.empty((nq, n), dtype=torch.float32, device=self.device)
         idx = torch.empty((nq, k), dtype=torch.int64, device=self.device)
         top = torch.empty((nq, k), dtype=torch.float32, device=self.device)
-        cnt = torch.zeros((nq,), dtype=torch.int32, device=self.device)
+        # every path below writes the counts, except the empty cases
+        cnt = (torch.empty if (n and nq and k_kernel) else torch.zeros)((nq,), dtype=torch.int32, device=self.device)
         if n and nq:
             use_xyz = query_positions is not None and spatial_filter_distance > 0
             qp = None

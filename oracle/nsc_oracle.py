@@ -117,8 +117,10 @@ def project_with_intensity(points: np.ndarray, cfg: OracleConfig):
 
 
 # ------------------------------------------------------------------------ interpolation
-def interpolate_range_image(img: np.ndarray) -> np.ndarray:
-    """``interpolate_range_image(img, 'linear')`` (range_image.py:15-89).
+def interpolate_range_image(img: np.ndarray, method: str = "linear") -> np.ndarray:
+    """``interpolate_range_image(img, method)`` (range_image.py:15-89); the encoder uses 'linear'.
+    'nearest' (:66-75): a hole takes the valid pixel at the smallest circular distance, the first
+    one in ascending column order on a tie (``np.argmin``).
 
     Pass 1 (:33-64): in each row that has some but not all pixels > 0, every empty pixel
     is linearly interpolated along azimuth between its nearest valid neighbours, with the
@@ -135,6 +137,11 @@ def interpolate_range_image(img: np.ndarray) -> np.ndarray:
         if n_valid == 0 or n_valid == W:                                         # :37-43
             continue
         vi = np.flatnonzero(valid)                                               # :46
+        if method == "nearest":
+            for x in np.flatnonzero(~valid):                                     # :68-75
+                d = np.minimum(np.abs(vi - x), W - np.abs(vi - x))
+                out[r, x] = out[r, vi[np.argmin(d)]]
+            continue
         xp = np.concatenate([vi - W, vi, vi + W])                                # :55-59
         fp = np.tile(out[r][valid], 3)                                           # :47,60
         holes = np.flatnonzero(~valid)                                           # :50

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Golden vectors for interpolate_range_image(img, 'linear') of the UNMODIFIED reference on random
+"""Golden vectors for interpolate_range_image(img, 'linear' | 'nearest') of the UNMODIFIED reference on random
 sparse images (hole patterns the projected scans do not produce). Build container only:
 
     PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden_interp.py
@@ -30,7 +30,8 @@ def main():
     a = imgs[10]; a[:] = 0; a[7, 100:200] = 12.5  # one non-empty row feeds all the others
     imgs = np.stack(imgs)
     out = np.stack([interpolate_range_image(i, method="linear") for i in imgs])
-    np.savez_compressed(os.path.join(HERE, "interp_random.npz"), images=imgs, interpolated=out)
+    near = np.stack([interpolate_range_image(i, method="nearest") for i in imgs])
+    np.savez_compressed(os.path.join(HERE, "interp_random.npz"), images=imgs, interpolated=out, nearest=near)
     print(imgs.shape, "holes filled:", int(((imgs == 0) & (out != 0)).sum()))
 
 

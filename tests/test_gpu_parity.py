@@ -118,6 +118,9 @@ def test_interpolate_entry_matches_reference_vectors():
         np.testing.assert_array_equal(interpolate_range_image(g["range_image"]), g["interpolated"])
     g = np.load(os.path.join(GOLDEN_DIR, "interp_random.npz"))      # recorded from the reference
     np.testing.assert_array_equal(interpolate_range_image(g["images"]), g["interpolated"])
+    np.testing.assert_array_equal(interpolate_range_image(g["images"], method="nearest"), g["nearest"])
+    with pytest.raises(ValueError):
+        interpolate_range_image(g["images"][0], method="cubic")
     rng = np.random.default_rng(5)
     imgs = (rng.uniform(1, 60, (40, 16, 360)) * (rng.uniform(0, 1, (40, 16, 360)) > 0.7)).astype(np.float32)
     imgs[3, 4:9] = 0
@@ -127,8 +130,10 @@ def test_interpolate_entry_matches_reference_vectors():
     imgs[8, 2] = 0
     imgs[8, 2, 77] = 5.5    # single valid pixel -> constant row
     got = interpolate_range_image(imgs)
+    near = interpolate_range_image(imgs, method="nearest")
     for i in range(len(imgs)):
         np.testing.assert_array_equal(got[i], orc.interpolate_range_image(imgs[i]))
+        np.testing.assert_array_equal(near[i], orc.interpolate_range_image(imgs[i], method="nearest"))
 
 
 def test_forward_on_range_images():

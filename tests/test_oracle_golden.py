@@ -150,5 +150,6 @@ def test_oracle_matches_reference_for_other_constructor_arguments():
 
 def test_oracle_interpolation_matches_reference_on_random_sparse_images():
     g = np.load(os.path.join(GOLDEN_DIR, "interp_random.npz"))
-    for img, want in zip(g["images"], g["interpolated"]):
+    for img, want, near in zip(g["images"], g["interpolated"], g["nearest"]):
         np.testing.assert_array_equal(orc.interpolate_range_image(img), want)
+        np.testing.assert_array_equal(orc.interpolate_range_image(img, method="nearest"), near)
