@@ -59,7 +59,13 @@ def make_config(args, world):
     """The ``config`` object; identical for the GPU arm and the reference arm of one invocation."""
     return {"workload": workload_name(args.scans, args.shape, args.shuffle), "scans_per_gpu": args.scans,
             "l2": f"inputs (~{args.scans * SHAPE_GB[args.shape]:.1f} GB per GPU) larger than the 126 MB L2, no flush needed",
-            "gather": ("none (single GPU)" if world == 1 else args.gather), "encoder": ENCODER_DESC}
+            "gather": ("none (single GPU)" if world == 1 else gather_name(args)), "encoder": ENCODER_DESC}
+
+
+def gather_name(args):
+    if args.gather == "fused" and args.gather_lag:
+        return "fused, pipelined (the database of step s-1 is complete when step s is enqueued; all complete before the timed region ends)"
+    return args.gather
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -307,7 +313,7 @@ def run_other_configs(enc, dev, pool, cores, kind, peak, steps):
     return res
 
 
-def run_c5(enc, dev, rank, world, gather, total_scans, steps):
+def run_c5(enc, dev, rank, world, gather, lag, total_scans, steps):
     """BASELINE.json configs[4]: ``total_scans`` HDL-64 scans sharded over the ranks (strong
     scaling), descriptors gathered into the database replicated on every GPU; 256 oracle spot
     checks (every 391st scan) and a bit-comparison of every rank's database."""
@@ -319,15 +325,17 @@ def run_c5(enc, dev, rank, world, gather, total_scans, steps):
     from oracle import nsc_oracle as orc
     lo, hi = synth.shard_range(total_scans, world, rank)
     points, offsets = synth.make_batch_resident(synth.HDL64, lo, hi - lo, dev)
-    se = ShardedEncoder(enc, total_scans, mode=gather)
+    se = ShardedEncoder(enc, total_scans, mode=gather, lag=lag if gather == "fused" else 0)
     for _ in range(2):
         se.encode(points, offsets)
+    se.flush()
     dist.barrier()
     torch.cuda.synchronize(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        db = se.encode(points, offsets)
+        se.encode(points, offsets)
+    db = se.flush()
     e1.record()
     dist.barrier()
     torch.cuda.synchronize(dev)
@@ -353,7 +361,8 @@ def run_c5(enc, dev, rank, world, gather, total_scans, steps):
     dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     rec = {"workload": f"{total_scans} HDL-64 scans sharded over {world} GPUs, descriptors gathered into the replicated database",
-           "scaling": "strong", "scans": total_scans, "gather": gather, "steps": steps,
+           "scaling": "strong", "scans": total_scans, "gather": gather, "gather_lag": lag if gather == "fused" else 0,
+           "steps": steps,
            "ms_per_pass": float(ms.item()), "value": total_scans / (float(ms.item()) * 1e-3), "unit": UNIT,
            "points_per_gpu": int(points.shape[0]), "db_bytes": int(db.numel() * 4),
            "db_identical": bool(int(same.item()) == 1), "oracle_spot": int(stats[1].item()),
@@ -414,7 +423,8 @@ def run_gpu_arm(args):
     sharded = None
     if world > 1:
         try:
-            sharded = ShardedEncoder(enc, world * n_scans, mode=args.gather)
+            sharded = ShardedEncoder(enc, world * n_scans, mode=args.gather,
+                                     lag=args.gather_lag if args.gather == "fused" else 0)
         except Exception as exc:   # symmetric memory unavailable on this box: use the NCCL gather
             if args.gather != "fused":
                 raise
@@ -439,8 +449,13 @@ def run_gpu_arm(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def flush():
+        if sharded is not None:
+            sharded.flush()
+
     for _ in range(args.warmup):
         step()
+    flush()
     barrier()
 
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ
@@ -448,14 +463,17 @@ def run_gpu_arm(args):
     sampler.start()
     stream = torch.cuda.current_stream(dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    end = torch.cuda.Event(enable_timing=True)
     barrier()
     for k in range(args.steps):
         ev[2 * k].record(stream)
         step()
         ev[2 * k + 1].record(stream)
+    flush()                      # pipelined gather: the last step's database completes inside the timed region
+    end.record(stream)
     barrier()
     clocks = sampler.stop()
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = ev[0].elapsed_time(end)
     step_ms = [ev[2 * k].elapsed_time(ev[2 * k + 1]) for k in range(args.steps)]
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -466,8 +484,48 @@ def run_gpu_arm(args):
     # the fused kernel alone (same launches, N=1 path) for the roofline; leaves the single-GPU
     # encode of this rank's block in `out`
     kern_avg_ms = sum(step_ms) / len(step_ms)
+    breakdown = None
     if world > 1:
         kern_avg_ms, _ = time_encode(enc, points, offsets, out, args.steps, 0)
+        # where the step time goes: every rank's plain kernel (GPUs of one box differ by a few %,
+        # and a step ends when the slowest rank has stored), and the kernel with the peer stores
+        # but without the signal-and-wait that ends a step
+        def loop_ms(fn, n):
+            barrier()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record(stream)
+            for _ in range(n):
+                fn()
+            e[1].record(stream)
+            barrier()
+            return e[0].elapsed_time(e[1]) / n
+
+        # interleaved rounds, so that drift of the box hits the three variants alike
+        plain, fused, full = [], [], []
+        n_loop = max(10, args.steps)
+        for _ in range(2):
+            plain.append(loop_ms(lambda: enc.encode_points_batch(points, offsets, out=out), n_loop))
+            if args.gather == "fused":
+                fused.append(loop_ms(lambda: sharded.encode(points, offsets, wait=False), n_loop))
+                sharded.encode(points, offsets)      # a complete step again (flags and buffers in step)
+                flush()
+            full.append(loop_ms(lambda: sharded.encode(points, offsets), n_loop))
+            flush()
+        enc.encode_points_batch(points, offsets, out=out)
+        barrier()
+        med = lambda v: min(v) if v else None
+        fused_ms = med(fused) if fused else med(plain)
+        mine = torch.tensor([med(plain), fused_ms, med(full)], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        breakdown = {"step_ms": total_ms / args.steps,
+                     "how": f"after the timed region: 2 interleaved rounds of {n_loop} launches of each variant, best of the two, ms per launch",
+                     "kernel_ms_per_rank": [float(t[0]) for t in allr],
+                     "kernel_with_peer_stores_ms_per_rank": [float(t[1]) for t in allr],
+                     "full_step_ms_per_rank": [float(t[2]) for t in allr],
+                     "note": "step = slowest rank's kernel with peer stores + one signal-and-wait kernel; "
+                             "weak-scaling efficiency against ONE GPU cannot exceed that GPU's kernel time / the "
+                             "slowest rank's"}
     peak, peak_src = hbm_peak()
     achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9
     traffic, traffic_src = None, "not captured for this shape (ncu --set full is a separate, profiler-run pass)"
@@ -489,7 +547,7 @@ def run_gpu_arm(args):
     ids = sorted(set(int(x) for x in np.linspace(0, n_scans - 1, 8 if world == 1 else 4)))
     db = None
     if sharded is not None:
-        db = sharded.db[:world * n_scans]
+        db = sharded.flush()[:world * n_scans]
         rows = db[rank * sharded.per: rank * sharded.per + n_scans]      # the timed output, this rank's block
         want = torch.empty((world * sharded.per, enc.output_dim), dtype=torch.float32, device=dev)
         local = torch.zeros((sharded.per, enc.output_dim), dtype=torch.float32, device=dev)
@@ -589,7 +647,7 @@ def run_gpu_arm(args):
             other = run_other_configs(enc, dev, pool, cores, kind, peak, max(3, min(args.steps, 10)))
             checks["ok"] = bool(checks["ok"] and all(c["checks"]["ok"] for c in other))
         else:
-            c5 = run_c5(enc, dev, rank, world, args.gather, args.c5_scans, 3)
+            c5 = run_c5(enc, dev, rank, world, args.gather, args.gather_lag, args.c5_scans, 3)
             checks["ok"] = bool(checks["ok"] and c5["ok"])
 
     cpu_baseline = None
@@ -621,8 +679,10 @@ def run_gpu_arm(args):
             "config": make_config(args, world),
             "workload_stats": {"points_per_gpu": total_points, "input_bytes_per_gpu": 16 * total_points},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "checks": checks,
-            "gpu_launches": args.steps, "clocks": clocks,
+            "gpu_launches": args.steps * (1 if world == 1 or args.gather != "fused" else 2), "clocks": clocks,
         }
+        if breakdown is not None:
+            line["scaling_breakdown"] = breakdown
         if other is not None:
             line["configs"] = other
         if c5 is not None:
@@ -711,6 +771,8 @@ def main():
     ap.add_argument("--e2e-scans", type=int, default=1024, help="scans per end-to-end step")
     ap.add_argument("--c5-scans", type=int, default=100000, help="N > 1: total scans of the sharded config")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
+    ap.add_argument("--gather-lag", type=int, default=1, choices=[0, 1],
+                    help="fused gather: 1 = pipelined (wait for the previous step's peers only), 0 = every step complete on return")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true",
                     help="headline line only: skip the other configs, the per-scan call pattern and the H2D ceiling")

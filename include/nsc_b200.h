@@ -126,17 +126,23 @@ int nsc_encode_batch_peers(const float* d_points, int point_stride, const int64_
                            const int32_t* h_lut, float* const* h_peer_db, int n_peers,
                            int64_t db_row0, void* d_workspace, size_t workspace_bytes, void* stream);
 
-/* The synchronisation that ends a fused multi-GPU step, as ONE small kernel on `stream` (after
- * the nsc_encode_batch_peers launch): tells every peer "rank `rank` has stored step `value`" by
- * a system-scope release store into the peer's flag array, then spins with system-scope acquire
- * loads until every peer has said the same to this rank. h_peer_flags[p]: device pointer
- * (peer-mapped) to rank p's array of n_peers uint32 flags, zero before the first step; `value`
- * must grow by one per step. With the step's database double-buffered by the caller (step s
- * writes buffer s & 1) no barrier is needed BEFORE the encode: a rank that returns from the wait
- * of step s-1 knows every peer has passed, in stream order, everything it enqueued before its own
- * step s-1 -- including whatever read buffer s & 1 after step s-2. */
-int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, uint32_t value,
-                         void* stream);
+/* The synchronisation of a fused multi-GPU step, as ONE small kernel on `stream` (after the
+ * nsc_encode_batch_peers launch): tells every peer "rank `rank` has stored step signal_value" by a
+ * system-scope release store into the peer's flag array, then spins with system-scope acquire
+ * loads until every peer has announced at least wait_value. h_peer_flags[p]: device pointer
+ * (peer-mapped) to rank p's array of n_peers uint32 flags, zero before the first step;
+ * signal_value must grow by one per step.
+ *   wait_value == signal_value      the step's database is complete when the kernel ends. With the
+ *       database double-buffered by the caller (step s writes buffer s & 1) no barrier is needed
+ *       BEFORE the encode: a rank that returns from the wait of step s-1 knows every peer has
+ *       passed, in stream order, everything it enqueued before its own step s-1 -- including
+ *       whatever read buffer s & 1 after step s-2.
+ *   wait_value == signal_value - 1  a rank may run one step ahead of the slowest peer (the wait
+ *       practically never blocks); step s-1 is complete when the kernel ends. Needs FOUR buffers
+ *       (step s writes buffer s & 3): leaving the wait for s-2 means every peer has finished its
+ *       own step s-2, which it started after consuming step s-4. */
+int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, uint32_t signal_value,
+                         uint32_t wait_value, void* stream);
 
 /* Replaces RangeImageProjector.project(points, keep_intensity=False)[0]
  * (stage = NSC_STAGE_PROJECTED) optionally followed by interpolate_range_image

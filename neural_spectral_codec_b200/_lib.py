@@ -66,7 +66,7 @@ SYMBOLS = {
     "nsc_workspace_bytes": (_SZ, [_I, _PP]),
     "nsc_encode_batch": (_I, [_VP, _I, _VP, _I64, _I, _PP, _VP, _VP, _VP, _SZ, _VP]),
     "nsc_encode_batch_peers": (_I, [_VP, _I, _VP, _I64, _I, _PP, _VP, _VP, _I, _I64, _VP, _SZ, _VP]),
-    "nsc_peer_signal_wait": (_I, [_VP, _I, _I, C.c_uint32, _VP]),
+    "nsc_peer_signal_wait": (_I, [_VP, _I, _I, C.c_uint32, C.c_uint32, _VP]),
     "nsc_project_batch": (_I, [_VP, _I, _VP, _I64, _I, _PP, _I, _VP, _VP, _SZ, _VP]),
     "nsc_project_intensity_batch": (_I, [_VP, _VP, _I64, _I, _PP, _VP, _VP, _VP]),
     "nsc_encode_range_images": (_I, [_VP, _I, _I, _PP, _VP, _VP, _VP]),

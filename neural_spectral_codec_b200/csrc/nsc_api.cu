@@ -81,22 +81,23 @@ struct PeerFlags {
 // Thread p: release-store `value` into peer p's flag of this rank, then acquire-poll this rank's
 // flag of peer p. Everything enqueued before this kernel on the stream (the encode kernel's peer
 // stores) is complete, and made visible system-wide by the fence, before any flag is raised.
-__global__ void peer_signal_wait_kernel(PeerFlags f, int n_peers, int rank, uint32_t value) {
+__global__ void peer_signal_wait_kernel(PeerFlags f, int n_peers, int rank, uint32_t signal_value,
+                                        uint32_t wait_value) {
     const int p = threadIdx.x;
     if (p >= n_peers) return;
     __threadfence_system();
     uint32_t* theirs = f.ptr[p] + rank;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(value) : "memory");
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(signal_value) : "memory");
     const uint32_t* mine = f.ptr[rank] + p;
     uint32_t seen;
     do {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
-    } while ((int32_t)(seen - value) < 0);      // wrap-safe "seen < value"
+    } while ((int32_t)(seen - wait_value) < 0);      // wrap-safe "seen < wait_value"
 }
 }  // namespace
 
-int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, uint32_t value,
-                         void* stream) {
+int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, uint32_t signal_value,
+                         uint32_t wait_value, void* stream) {
     if (n_peers < 1 || n_peers > NSC_MAX_PEERS || rank < 0 || rank >= n_peers) return NSC_ERR_BAD_COUNT;
     if (!h_peer_flags) return NSC_ERR_NULL_POINTER;
     PeerFlags f;
@@ -104,7 +105,7 @@ int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, u
         f.ptr[i] = i < n_peers ? h_peer_flags[i] : nullptr;
         if (i < n_peers && !f.ptr[i]) return NSC_ERR_NULL_POINTER;
     }
-    peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n_peers, rank, value);
+    peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n_peers, rank, signal_value, wait_value);
     return record_cuda(cudaGetLastError());
 }
 

@@ -415,6 +415,7 @@ encode_points_kernel(const __grid_constant__ EncodeArgs a, const __grid_constant
         NSC_PHASE(1);
         finish_scan(a, dp, S, scan, phase_t0);
     }
+    if (tid == 0) wait_bulk_stores_done();      // descriptors leave shared memory before the CTA does
 }
 
 // ---- warp-specialised persistent kernel ---------------------------------------------------
@@ -702,6 +703,7 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
         G::sync();         // S.red / S.hist / S.src are rewritten by the next scan's tail
         if (gt == 0) mail[16] = k + 1;                    // tail_done
     }
+    if (gt == 0) wait_bulk_stores_done();                 // descriptors leave shared memory before the CTA does
 }
 
 template <int ROWMODE>
@@ -797,6 +799,7 @@ encode_points_split_kernel(const __grid_constant__ EncodeArgs a, const __grid_co
         __syncthreads();
         long long phase_t0 = 0;
         finish_scan(a, dp, S, scan, phase_t0);
+        if (tid == 0) wait_bulk_stores_done();
     }
 }
 
@@ -825,6 +828,7 @@ encode_images_kernel(const float* __restrict__ images, int n_images, int rows,
         spectrum_and_bins(S, dp, rows);
         normalise_and_store(S, dp, out + (long long)im * D, none, 0);
     }
+    if (threadIdx.x == 0) wait_bulk_stores_done();
 }
 
 // interpolate_range_image on device images (range_image.py:15-89).

@@ -209,6 +209,23 @@ __device__ __forceinline__ void rows_to_filled(const TailSmem& S, int rows, bool
     G::sync();
 }
 
+// Descriptor stores as bulk copies shared -> global (TMA, SASS UBLKCP.G.S): the normalised
+// descriptor is written in place over S.hist and ONE thread sends the 3.2 KB to the local output
+// and to every peer's database -- over NVLink for the remote ones -- instead of every thread
+// storing every element 1 + n_peers times. wait_bulk_stores_read() must precede the next write to
+// S.hist by any thread (called by the issuing thread before a group barrier that all pass).
+__device__ __forceinline__ void bulk_store_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                 "r"((uint32_t)__cvta_generic_to_shared(src_smem)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void wait_bulk_stores_read() {
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void wait_bulk_stores_done() {
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // Value of target row i at column n: the stored row, or the mean of its source rows when the
 // image height differs from T (adaptive_avg_pool2d on (1,1,rows,360) -> (T,360)).
 __device__ __forceinline__ float pooled_value(const TailSmem& S, int rows, int T, int i, int n) {
@@ -245,6 +262,10 @@ __device__ __forceinline__ void spectrum_and_bins(const TailSmem& S, const P& dp
     const int T = dp.T, nb = dp.n_bins;
     const int n_sig_total = (T + 1) / 2;
     const int cap = n_sig_total < kMaxSignals ? n_sig_total : kMaxSignals;
+    // the previous descriptor may still be on its way out of S.hist (bulk stores of
+    // normalise_and_store): the thread that issued them waits here; every other thread passes at
+    // least one group barrier below before S.hist is written again
+    if (G::tid() == 0) wait_bulk_stores_read();
     float* mag = reinterpret_cast<float*>(S.fa);           // 2 * n_sig x 181, valid after the last pass
     for (int g0 = 0; g0 < n_sig_total; g0 += cap) {
         const int n_sig = min(cap, n_sig_total - g0);
@@ -317,6 +338,20 @@ __device__ __forceinline__ void normalise_and_store(const TailSmem& S, const P& 
     const float total = (float)tot;
     const bool ok = total > dp.eps;
     const float denom = __fadd_rn(total, dp.eps);
+    // bulk path: 16-byte granularity of size and of every destination row
+    bool bulk = ((D * 4) & 15) == 0 && (out == nullptr || (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int p = 0; p < peers.n; ++p) bulk = bulk && (reinterpret_cast<uintptr_t>(peers.ptr[p]) & 15) == 0;
+    if (bulk) {
+        for (int i = G::tid(); i < D; i += G::kSize) S.hist[i] = ok ? __fdiv_rn(S.hist[i], denom) : dp.uniform;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async-proxy reads
+        G::sync();
+        if (G::tid() == 0) {
+            if (out) bulk_store_s2g(out, S.hist, (uint32_t)D * 4u);
+            for (int p = 0; p < peers.n; ++p) bulk_store_s2g(peers.ptr[p] + peer_row * D, S.hist, (uint32_t)D * 4u);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        return;
+    }
     for (int i = G::tid(); i < D; i += G::kSize) {
         const float v = ok ? __fdiv_rn(S.hist[i], denom) : dp.uniform;
         if (out) out[i] = v;

@@ -47,11 +47,19 @@ def gather_descriptors(local: torch.Tensor, n_scans: int, group=None) -> torch.T
 
 
 class ShardedEncoder:
-    """Encodes this rank's block of a global batch and keeps the replicated database."""
+    """Encodes this rank's block of a global batch and keeps the replicated database.
 
-    def __init__(self, encoder, n_scans: int, mode: str = "nccl", group=None):
+    ``mode="fused"``, ``lag=0``: ``encode`` returns the database of THIS step (complete in stream
+    order). ``lag=1`` pipelines the gather: ``encode`` enqueues step s and waits only for step
+    s-1, so a rank is never held up by the slowest peer of the current step; it returns the
+    database of step s-1 (``None`` on the first call) and ``flush()`` completes the last one.
+    Four database buffers instead of two (see ``nsc_peer_signal_wait`` in the header)."""
+
+    def __init__(self, encoder, n_scans: int, mode: str = "nccl", group=None, lag: int = 0):
         if mode not in ("nccl", "fused"):
             raise ValueError("mode must be 'nccl' or 'fused'")
+        if lag not in (0, 1) or (lag and mode != "fused"):
+            raise ValueError("lag must be 0, or 1 with mode='fused'")
         self.encoder = encoder
         self.n_scans = int(n_scans)
         self.group = group
@@ -60,6 +68,7 @@ class ShardedEncoder:
         self.lo, self.hi = shard_range(self.n_scans, self.world, self.rank)
         self.per = padded_rows(self.n_scans, self.world)
         self.mode = mode
+        self.lag = lag
         self.D = encoder.output_dim
         dev = encoder.alpha.device
         if dev.type != "cuda":
@@ -73,12 +82,13 @@ class ShardedEncoder:
             import torch.distributed._symmetric_memory as symm
             gname = (group or dist.group.WORLD).group_name
             rows = self.world * self.per
-            self._dbs = symm.empty((2, rows, self.D), dtype=torch.float32, device=dev)   # ping-pong
+            self._nbuf = 4 if lag else 2
+            self._dbs = symm.empty((self._nbuf, rows, self.D), dtype=torch.float32, device=dev)
             self._dbs.zero_()
             self._hdl = symm.rendezvous(self._dbs, gname)
-            half = rows * self.D * 4
-            self._peer_ptrs = [(C.c_void_p * self.world)(*[int(self._hdl.buffer_ptrs[r]) + b * half
-                                                           for r in range(self.world)]) for b in (0, 1)]
+            one = rows * self.D * 4
+            self._peer_ptrs = [(C.c_void_p * self.world)(*[int(self._hdl.buffer_ptrs[r]) + b * one
+                                                           for r in range(self.world)]) for b in range(self._nbuf)]
             self._flags = symm.empty((64,), dtype=torch.int32, device=dev)
             self._flags.zero_()
             self._flag_hdl = symm.rendezvous(self._flags, gname)
@@ -86,15 +96,33 @@ class ShardedEncoder:
                                                           for r in range(self.world)])
             self._flag_hdl.barrier()          # every rank's flags are zero before anyone signals
             torch.cuda.synchronize(dev)
-            self._step = 0
+            self._step = 0                    # steps enqueued
+            self._complete = 0                # steps whose database is complete in stream order
             self.db = self._dbs[0]
             self._ws = torch.empty(64, dtype=torch.int32, device=dev)
             self.local = None
 
-    def encode(self, points: torch.Tensor, offsets: torch.Tensor) -> torch.Tensor:
-        """``points`` / ``offsets`` describe THIS rank's scans ``[lo, hi)``. Returns the
-        replicated ``(n_scans, D)`` database (valid on return for "nccl"; for "fused" after
-        the barrier this method issues)."""
+    def _signal_wait(self, wait_value: int) -> None:
+        with torch.cuda.device(self.device):
+            st = _lib.load().nsc_peer_signal_wait(self._flag_ptrs, self.world, self.rank, self._step, wait_value,
+                                                  torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(st, "nsc_peer_signal_wait")
+        self._complete = max(self._complete, wait_value)
+        if self._complete:
+            self.db = self._dbs[(self._complete - 1) % self._nbuf]
+
+    def flush(self) -> torch.Tensor:
+        """Completes every enqueued step (a no-op unless ``lag=1``) and returns the database."""
+        if self.mode == "fused" and self._complete < self._step:
+            self._signal_wait(self._step)
+        return self.db[:self.n_scans]
+
+    def encode(self, points: torch.Tensor, offsets: torch.Tensor, wait: bool = True):
+        """``points`` / ``offsets`` describe THIS rank's scans ``[lo, hi)``. Returns the latest
+        complete replicated ``(n_scans, D)`` database in stream order: this step's (``lag=0``) or
+        the previous step's (``lag=1``; ``None`` before there is one). ``wait=False`` (fused mode,
+        measurements only) skips the synchronisation kernel: the caller must synchronise all
+        ranks before the next call."""
         n_local = self.hi - self.lo
         if offsets.numel() - 1 != n_local:
             raise ValueError(f"rank {self.rank} owns {n_local} scans, got {offsets.numel() - 1}")
@@ -102,26 +130,24 @@ class ShardedEncoder:
             if n_local:
                 self.encoder.encode_points_batch(points, offsets, out=self.local[:n_local])
             dist.all_gather_into_tensor(self.db, self.local, group=self.group)
-        else:
-            lib = _lib.load()
-            from .encoder import _check_batch
-            points, offsets, n, stride = _check_batch(points, offsets)
-            # Peers store into this rank's database from THEIR streams. Step s fills buffer s & 1:
-            # a rank that has left the wait of step s-1 knows every peer is past (in stream order)
-            # whatever read that buffer after step s-2, so the stores below need no barrier first.
-            b = self._step & 1
-            p = self.encoder._params()
-            lut = self.encoder.freq_to_bin()
-            stream = torch.cuda.current_stream(self.device).cuda_stream
-            with torch.cuda.device(self.device):
-                st = lib.nsc_encode_batch_peers(
-                    points.data_ptr(), stride, offsets.data_ptr(), 0, n, C.byref(p),
-                    lut.ctypes.data, self._peer_ptrs[b], self.world, self.rank * self.per,
-                    self._ws.data_ptr(), self._ws.numel() * 4, stream)
-                _lib.check(st, "nsc_encode_batch_peers")
-                self._step += 1
-                st = lib.nsc_peer_signal_wait(self._flag_ptrs, self.world, self.rank, self._step, stream)
-            _lib.check(st, "nsc_peer_signal_wait")
-            self.db = self._dbs[b]
+            return self.db[:self.n_scans]
+        lib = _lib.load()
+        from .encoder import _check_batch
+        points, offsets, n, stride = _check_batch(points, offsets)
+        # Peers store into this rank's database from THEIR streams. Step s fills buffer s mod 2
+        # (mod 4 with lag): a rank that has left the wait for step s-1 (s-2) knows every peer is
+        # past, in stream order, whatever read that buffer last, so no barrier precedes the stores.
+        b = self._step % self._nbuf
+        p = self.encoder._params()
+        lut = self.encoder.freq_to_bin()
+        with torch.cuda.device(self.device):
+            st = lib.nsc_encode_batch_peers(
+                points.data_ptr(), stride, offsets.data_ptr(), 0, n, C.byref(p),
+                lut.ctypes.data, self._peer_ptrs[b], self.world, self.rank * self.per,
+                self._ws.data_ptr(), self._ws.numel() * 4, torch.cuda.current_stream(self.device).cuda_stream)
+        _lib.check(st, "nsc_encode_batch_peers")
+        if wait:
+            self._step += 1
+            self._signal_wait(self._step - self.lag)
         # rank r owns global rows [r*per, r*per + n_r): the database is contiguous in scan index
-        return self.db[:self.n_scans]
+        return self.db[:self.n_scans] if self._complete else None

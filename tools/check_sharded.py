@@ -33,15 +33,20 @@ def main():
     full_pts, full_offs = synth.make_batch(shape, 0, n, device=dev)
     want = enc.encode_points_batch(full_pts, full_offs)
     ok = True
-    for mode in ("nccl", "fused"):
-        se = ShardedEncoder(enc, n, mode=mode)
-        for rep in range(3):
+    for mode, lag in (("nccl", 0), ("fused", 0), ("fused", 1)):
+        se = ShardedEncoder(enc, n, mode=mode, lag=lag)
+        for rep in range(5):
             db = se.encode(pts, offs)
+            if lag:
+                assert (db is None) == (rep == 0)
+                db = se.flush() if rep % 2 else db
+            if db is None:
+                continue
             torch.cuda.synchronize()
             same = bool(torch.equal(db, want))
             ok &= same
             if rank == 0 or not same:
-                print(f"rank {rank} mode {mode} rep {rep}: database == single-GPU encode: {same}", flush=True)
+                print(f"rank {rank} mode {mode} lag {lag} rep {rep}: database == single-GPU encode: {same}", flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
