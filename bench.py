@@ -771,7 +771,7 @@ def main():
     ap.add_argument("--e2e-scans", type=int, default=1024, help="scans per end-to-end step")
     ap.add_argument("--c5-scans", type=int, default=100000, help="N > 1: total scans of the sharded config")
     ap.add_argument("--gather", default="fused", choices=["nccl", "fused"])
-    ap.add_argument("--gather-lag", type=int, default=1, choices=[0, 1],
+    ap.add_argument("--gather-lag", type=int, default=0, choices=[0, 1],
                     help="fused gather: 1 = pipelined (wait for the previous step's peers only), 0 = every step complete on return")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
     ap.add_argument("--no-extras", action="store_true",

@@ -196,6 +196,15 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
                         int64_t n_points, const int64_t* h_offsets, int n_scans,
                         const nsc_params* p, const int32_t* h_lut, float* h_out);
 
+/* ONE scan from pageable host memory to a descriptor on the DEVICE, on the caller's stream -- the
+ * reference's own call shape: encoder.encode_points(numpy_scan) per scan (pipeline.py:245,
+ * :336-354, train_multi_dataset.py:182), whose result lives on alpha.device. The scan is staged
+ * through pinned memory in pieces that overlap with their DMA; the fused kernel follows on
+ * `stream`. Returns as soon as h_points may be reused; d_out (float32[target_rows * n_bins]) is
+ * complete in stream order. n_points <= max_chunk_points of the pipeline. */
+int nsc_pipeline_encode_scan(nsc_pipeline* pl, const float* h_points, int point_stride, int64_t n_points,
+                             const nsc_params* p, const int32_t* h_lut, float* d_out, void* stream);
+
 /* The same for scans that live in SEPARATE host arrays, as the reference's loaders hand them
  * out one np.fromfile() at a time (kitti_loader.py:100-115) -- the loop of pipeline.py:336-354
  * without concatenating first. h_scans[i] points to h_counts[i] points of point_stride floats

@@ -74,6 +74,7 @@ SYMBOLS = {
     "nsc_pipeline_create": (_I, [_I64, _I, _I, C.POINTER(_VP)]),
     "nsc_pipeline_destroy": (None, [_VP]),
     "nsc_pipeline_encode": (_I, [_VP, _VP, _I, _I64, _VP, _I, _PP, _VP, _VP]),
+    "nsc_pipeline_encode_scan": (_I, [_VP, _VP, _I, _I64, _PP, _VP, _VP, _VP]),
     "nsc_pipeline_encode_scans": (_I, [_VP, _VP, _VP, _I, _I, _PP, _VP, _VP]),
     "nsc_voxel_overlap_workspace_bytes": (_SZ, [_I64, _I64, _I]),
     "nsc_voxel_overlap_batch": (_I, [_VP, _I, _I, _VP, _I64, _I64, _VP, _I, C.c_double, _VP, _VP, _VP, _SZ, _VP]),

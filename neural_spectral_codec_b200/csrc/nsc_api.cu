@@ -170,6 +170,7 @@ struct nsc_pipeline {
         float* h_out;          // pinned chunk descriptors
         bool busy;
     } slot[4];
+    unsigned next_single;      // rotation of nsc_pipeline_encode_scan over the slots
 };
 
 static const int kMaxChunkScans = 1024;
@@ -355,10 +356,9 @@ int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, con
     // pinned staging for every slot, allocated on the first call of this entry point
     for (int i = 0; i < pl->n_buffers; ++i) {
         nsc_pipeline::Slot& s = pl->slot[i];
-        if (s.h_stage) continue;
-        if ((e = cudaHostAlloc(&s.h_stage, (size_t)pl->max_chunk_points * 16, cudaHostAllocDefault)) != cudaSuccess ||
-            (e = cudaHostAlloc(&s.h_offsets, (size_t)(kMaxChunkScans + 1) * 8, cudaHostAllocDefault)) != cudaSuccess ||
-            (e = cudaHostAlloc(&s.h_out, (size_t)kMaxChunkScans * kMaxDescriptor * 4, cudaHostAllocDefault)) != cudaSuccess) {
+        if ((!s.h_stage && (e = cudaHostAlloc(&s.h_stage, (size_t)pl->max_chunk_points * 16, cudaHostAllocDefault)) != cudaSuccess) ||
+            (!s.h_offsets && (e = cudaHostAlloc(&s.h_offsets, (size_t)(kMaxChunkScans + 1) * 8, cudaHostAllocDefault)) != cudaSuccess) ||
+            (!s.h_out && (e = cudaHostAlloc(&s.h_out, (size_t)kMaxChunkScans * kMaxDescriptor * 4, cudaHostAllocDefault)) != cudaSuccess)) {
             cudaSetDevice(prev);
             return record_cuda(e);
         }
@@ -409,6 +409,57 @@ int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, con
     for (int i = 0; i < pl->n_buffers; ++i) {
         if (st == NSC_OK) st = retire(i);
         else { cudaStreamSynchronize(pl->slot[i].stream); pl->slot[i].busy = false; }
+    }
+    cudaSetDevice(prev);
+    return st;
+}
+
+// One scan from pageable host memory to a descriptor ON THE DEVICE, on the caller's stream: the
+// reference's call shape (one encode_points(numpy) per scan, pipeline.py:336-354). The scan is
+// copied into pinned staging in 512 KB pieces, each handed to the copy engine as soon as it is
+// staged, so the CPU copy of piece i+1 overlaps the DMA of piece i; the kernel follows on the
+// same stream. Returns when the source array may be reused; nothing else is synchronised (a slot
+// is reused only after the work that read its staging has finished).
+int nsc_pipeline_encode_scan(nsc_pipeline* pl, const float* h_points, int point_stride, int64_t n_points,
+                             const nsc_params* p, const int32_t* h_lut, float* d_out, void* stream) {
+    if (!pl) return NSC_ERR_NULL_POINTER;
+    DeviceParams dp;
+    int st = make_device_params(p, h_lut, &dp);
+    if (st != NSC_OK) return st;
+    if (point_stride != 3 && point_stride != 4) return NSC_ERR_BAD_STRIDE;
+    if (n_points < 0) return NSC_ERR_BAD_COUNT;
+    if (n_points > pl->max_chunk_points) return NSC_ERR_WORKSPACE;
+    if ((n_points && !h_points) || !d_out) return NSC_ERR_NULL_POINTER;
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) return record_cuda(e);
+    if ((e = cudaSetDevice(pl->device)) != cudaSuccess) return record_cuda(e);
+    nsc_pipeline::Slot& s = pl->slot[pl->next_single++ % pl->n_buffers];
+    cudaStream_t cs = (cudaStream_t)stream;
+    auto fail = [&](cudaError_t err) { cudaSetDevice(prev); return record_cuda(err); };
+    if (!s.h_stage && (e = cudaHostAlloc(&s.h_stage, (size_t)pl->max_chunk_points * 16, cudaHostAllocDefault)) != cudaSuccess)
+        return fail(e);
+    if (!s.h_offsets && (e = cudaHostAlloc(&s.h_offsets, (size_t)(kMaxChunkScans + 1) * 8, cudaHostAllocDefault)) != cudaSuccess)
+        return fail(e);
+    if (s.busy) {           // the previous use of this slot's staging and device buffers
+        if ((e = cudaEventSynchronize(s.done)) != cudaSuccess) return fail(e);
+        s.busy = false;
+    }
+    s.h_offsets[0] = 0;
+    s.h_offsets[1] = n_points;
+    if ((e = cudaMemcpyAsync(s.d_offsets, s.h_offsets, 16, cudaMemcpyHostToDevice, cs)) != cudaSuccess) return fail(e);
+    const size_t bytes = (size_t)n_points * point_stride * 4, piece = 512 << 10;
+    for (size_t off = 0; off < bytes; off += piece) {
+        const size_t len = bytes - off < piece ? bytes - off : piece;
+        memcpy((char*)s.h_stage + off, (const char*)h_points + off, len);
+        if ((e = cudaMemcpyAsync((char*)s.d_points + off, (char*)s.h_stage + off, len, cudaMemcpyHostToDevice, cs)) !=
+            cudaSuccess)
+            return fail(e);
+    }
+    st = launch_encode(s.d_points, point_stride, s.d_offsets, 0, 1, dp, d_out, nullptr, 0, nullptr, 0, 0, s.d_ws, cs);
+    if (st == NSC_OK) {
+        if ((e = cudaEventRecord(s.done, cs)) != cudaSuccess) return fail(e);
+        s.busy = true;
     }
     cudaSetDevice(prev);
     return st;

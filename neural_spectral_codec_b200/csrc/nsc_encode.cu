@@ -21,6 +21,13 @@ namespace {
 #ifndef NSC_PRECHECK
 #define NSC_PRECHECK 1
 #endif
+// L2 policy of the point stream: 1 = evict-first when the kernel has no peers (single-GPU
+// encode: +1 %, the points no longer push the descriptor lines out of L2), plain when descriptors
+// of 7 peers are landing in this GPU's memory (evict-first costs 3.5 % there, profiles/r2o_*);
+// 0 = never (tuning builds).
+#ifndef NSC_L2_HINTS
+#define NSC_L2_HINTS 1
+#endif
 constexpr int kUnroll = 4;   // independent 16-byte loads in flight per thread (LDG feed)
 
 struct EncodeArgs {
@@ -71,6 +78,22 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// The same with an L2 cache policy: the points are read exactly once, so they are marked
+// evict-first and do not push the (dirty) descriptor lines of this and the peer GPUs out of L2
+// while the kernel runs -- write-backs trickling into the read stream cost far more DRAM time
+// than their bytes (tools/peer_store_cost.py).
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(uint32_t dst, const void* src, uint32_t bytes,
+                                                   uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
         : "memory");
 }
 // global -> shared bulk copy, completion counted in bytes on an mbarrier.
@@ -522,6 +545,8 @@ __device__ __forceinline__ void ws_producer_role(const EncodeArgs& a, unsigned c
     const float4* p4 = reinterpret_cast<const float4*>(a.points);
     int scan = blockIdx.x;
     int next = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
+    const uint64_t pol = l2_policy_evict_first();
+    const bool hint = NSC_L2_HINTS != 0 && a.peers.n == 0;
     uint32_t slot = 0, phase = 0;                     // phase = (stage counter / kWsDepth) & 1
     bool wrapped = false;
     for (int k = 0;; ++k) {
@@ -543,7 +568,8 @@ __device__ __forceinline__ void ws_producer_role(const EncodeArgs& a, unsigned c
             if (wrapped) mbar_wait(bars.slot_empty(slot), phase ^ 1);
             const uint32_t bytes = (uint32_t)min(kWsStagePoints, n - base) * 16u;
             mbar_expect_tx(bars.slot_full(slot), bytes);
-            bulk_copy_g2s(ring + slot * kWsSlotBytes, src + base, bytes, bars.slot_full(slot));
+            if (hint) bulk_copy_g2s_hint(ring + slot * kWsSlotBytes, src + base, bytes, bars.slot_full(slot), pol);
+            else bulk_copy_g2s(ring + slot * kWsSlotBytes, src + base, bytes, bars.slot_full(slot));
             if (++slot == kWsDepth) { slot = 0; phase ^= 1; wrapped = true; }
         }
         scan = next;

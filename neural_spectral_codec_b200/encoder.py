@@ -191,6 +191,8 @@ class SpectralEncoder(nn.Module):
         self._lut = None
         self._pipeline = None
         self._pipeline_key = None
+        self._scan_pipeline = None
+        self._scan_pipeline_key = None
 
     # ------------------------------------------------------------------ constants
     def _compute_bin_edges(self, alpha: torch.Tensor) -> torch.Tensor:
@@ -274,8 +276,29 @@ class SpectralEncoder(nn.Module):
                 pts = pts[:, :3]
             offs = torch.tensor([0, pts.shape[0]], dtype=torch.int64).to(dev)
         else:
-            pts, offs = _host_scan_to_device(points, dev)
+            return self._encode_host_scan(_as_f32_points(points), dev)
         return self.encode_points_batch(pts, offs)[0]
+
+    def _encode_host_scan(self, a: np.ndarray, dev: torch.device) -> torch.Tensor:
+        """One pageable numpy scan -> descriptor on the device through ``nsc_pipeline_encode_scan``
+        (pinned staging in pieces overlapped with their DMA, kernel on the current stream)."""
+        lib = _lib.load()
+        cap = max(1 << 18, int(a.shape[0]))
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), cap)
+        if self._scan_pipeline is None or self._scan_pipeline_key[0] != key[0] or self._scan_pipeline_key[1] < cap:
+            if self._scan_pipeline is not None:
+                lib.nsc_pipeline_destroy(self._scan_pipeline)
+                self._scan_pipeline = None
+            h = C.c_void_p()
+            _lib.check(lib.nsc_pipeline_create(cap, 3, key[0], C.byref(h)), "nsc_pipeline_create")
+            self._scan_pipeline, self._scan_pipeline_key = h, key
+        out = torch.empty((self.output_dim,), dtype=torch.float32, device=dev)
+        p = self._params()
+        lut = self.freq_to_bin()
+        st = lib.nsc_pipeline_encode_scan(self._scan_pipeline, a.ctypes.data, a.shape[1], a.shape[0], C.byref(p),
+                                          lut.ctypes.data, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(st, "nsc_pipeline_encode_scan")
+        return out
 
     def encode_scans(self, scans: Union[Sequence[np.ndarray], Tuple[np.ndarray, np.ndarray]],
                      out: Optional[np.ndarray] = None, max_chunk_points: int = 4_000_000,
@@ -342,6 +365,9 @@ class SpectralEncoder(nn.Module):
         if getattr(self, "_pipeline", None) is not None:
             _lib.load().nsc_pipeline_destroy(self._pipeline)
             self._pipeline, self._pipeline_key = None, None
+        if getattr(self, "_scan_pipeline", None) is not None:
+            _lib.load().nsc_pipeline_destroy(self._scan_pipeline)
+            self._scan_pipeline, self._scan_pipeline_key = None, None
 
     def __del__(self):
         try:
