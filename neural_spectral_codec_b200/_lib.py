@@ -99,10 +99,11 @@ def build(verbose: bool = False, tuning: bool = True) -> str:
     """Compile the CUDA sources for sm_100a into ``libnsc_b200.so`` (in-tree), and -- for the
     A/B tools and the bit-identity tests -- the tuning build ``libnsc_b200_tune.so``
     (``-DNSC_TUNING``: the only build that reads NSC_FEED / NSC_SPLIT / NSC_WS from the
-    environment; selected with ``NSC_LIB=<path>``)."""
+    environment; ``-DNSC_SEL_CAP=128``: a small candidate list, so that tests reach the overflow
+    path of the retrieval selection; selected with ``NSC_LIB=<path>``)."""
     cmds = [["make", "-C", CSRC, "-j4"]]
     if tuning:
-        cmds.append(["make", "-C", CSRC, "-j4", "VARIANT=tune", "DEFS=-DNSC_TUNING"])
+        cmds.append(["make", "-C", CSRC, "-j4", "VARIANT=tune", "DEFS=-DNSC_TUNING -DNSC_SEL_CAP=128"])
     for cmd in cmds:
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode != 0:

@@ -11,9 +11,10 @@
 //                          from above; each CTA collects the keys of its slice under the bound (a
 //                          few more than k in all), the last CTA of a query sorts them. ~5 us
 //                          instead of one CTA re-reading all N distances.
-//   topk_kernel            larger k, or a candidate overflow of select_kernel (massive ties): one
-//                          CTA per query, per-thread-minimum bound + candidate sort, 4-pass radix
-//                          select as the last resort
+//                          (a candidate overflow -- fewer than k finite group minima -- is
+//                          resolved by that CTA with an exact 8-pass radix select of the 64-bit keys)
+//   topk_kernel            128 < k <= 1024: one CTA per query, per-thread-minimum bound + candidate
+//                          sort, 4-pass radix select as the last resort
 #include <math.h>
 
 #include "nsc_internal.h"
@@ -131,25 +132,13 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
     constexpr int padded = PER * 32;
     float* qcdf = smem;                                           // Q x padded
     float* ring = smem + a.n_queries * padded + warp * (kRowStages * padded);
-    // query CDFs (wasserstein.py:152-154,165), one warp per query, staged through the ring
-    for (int q = warp; q < a.n_queries; q += kRWarps) {
-        for (int e = lane; e < padded; e += 32) ring[e] = e < a.n_bins ? a.queries[(long long)q * a.n_bins + e] : 0.0f;
-        __syncwarp();
-        float c[kMaxPerLane];
-        row_cdf<1>(ring, a.n_bins, PER, a.eps, lane, c);
-#pragma unroll
-        for (int i = 0; i < PER; ++i)      // padding lanes hold 0, like the padding of the database rows
-            qcdf[q * padded + lane * PER + i] = lane * PER + i < a.n_bins ? c[i] : 0.0f;
-        __syncwarp();
-    }
-    if (a.n_bins < padded)
-        for (int s = 0; s < kRowStages; ++s)
-            for (int e = a.n_bins + lane; e < padded; e += 32) ring[s * padded + e] = 0.0f;
-    __syncthreads();
-
     const long long n_warps = (long long)gridDim.x * kRWarps;
     const long long r0 = (long long)blockIdx.x * kRWarps + warp;
     const bool vec = (a.n_bins & 3) == 0;
+    if (a.n_bins < padded)
+        for (int s = 0; s < kRowStages; ++s)
+            for (int e = a.n_bins + lane; e < padded; e += 32) ring[s * padded + e] = 0.0f;
+    __syncwarp();
     auto issue = [&](long long r, int slot) {
         if (r < a.n_db) {
             const float* src = a.db_cdfs + r * a.n_bins;
@@ -162,8 +151,25 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    // the first rows are on their way while the query CDFs are built
 #pragma unroll
     for (int s = 0; s < kRowStages - 1; ++s) issue(r0 + s * n_warps, s);
+    // query CDFs (wasserstein.py:152-154,165), one warp per query, staged through the warp's
+    // slice of the area behind the rings
+    {
+        float* stage = smem + a.n_queries * padded + kRWarps * (kRowStages * padded) + warp * padded;
+        for (int q = warp; q < a.n_queries; q += kRWarps) {
+            for (int e = lane; e < padded; e += 32) stage[e] = e < a.n_bins ? a.queries[(long long)q * a.n_bins + e] : 0.0f;
+            __syncwarp();
+            float c[kMaxPerLane];
+            row_cdf<1>(stage, a.n_bins, PER, a.eps, lane, c);
+#pragma unroll
+            for (int i = 0; i < PER; ++i)      // padding lanes hold 0, like the padding of the database rows
+                qcdf[q * padded + lane * PER + i] = lane * PER + i < a.n_bins ? c[i] : 0.0f;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
     const bool spatial = a.db_xyz != nullptr && a.query_xyz != nullptr;
     int slot = 0;
     unsigned long long best[kMaxQueries];       // lane 0: smallest key of this warp's rows, per query
@@ -222,15 +228,18 @@ struct TopkArgs {
     long long* top_idx;       // Q x k, -1 padded
     float* top_dist;          // Q x k, +inf padded
     int* top_count;           // Q
-    int* only_if;             // null, or per-query flags: run only where set (and clear it)
 };
 
 // Workspace of the selection, per query: counters {candidates, CTAs done, overflow, pad}, then
 // kSelCap candidate keys, then the warp minima of the distance pass. Zero before the first call;
 // every call leaves the counters zero again.
-constexpr int kSelThreads = 256;
-constexpr int kSelCap = 1024;
+constexpr int kSelThreads = 256;      // == the radix of the fallback select
+#ifndef NSC_SEL_CAP
+#define NSC_SEL_CAP 1024               // the tuning build uses 128 so that the tests reach the overflow path
+#endif
+constexpr int kSelCap = NSC_SEL_CAP;
 constexpr int kSelMaxK = 128;
+static_assert(kSelCap >= kSelMaxK && kSelCap <= 1024 && (kSelCap & (kSelCap - 1)) == 0, "candidate list");
 constexpr int kSelCtas = 128;         // CTAs per query, at most
 struct SelectArgs {
     const float* distances;
@@ -333,19 +342,63 @@ select_kernel(const __grid_constant__ SelectArgs a) {
     if (!s_last) return;
     const int n_cand = s_count;
     if (tid == 0) { cnt[0] = 0; cnt[1] = 0; }              // leave the workspace clean for the next call
-    if (n_cand > kSelCap) {                                 // massive ties: the one-CTA kernel takes over
-        if (tid == 0) cnt[2] = 1;
-        return;
+    int n_have = n_cand;
+    if (n_cand > kSelCap) {
+        // More keys under the bound than the candidate list holds (fewer than k finite group
+        // minima, or rows clustered in few groups). Rare, so this CTA alone finds the exact k-th
+        // smallest key by an 8-pass radix select over all N keys -- they are distinct 64-bit
+        // values (distance bits, row), so there are no ties to order -- and collects the keys
+        // up to it.
+        __shared__ unsigned hist[256];
+        __shared__ unsigned long long s_prefix;
+        __shared__ unsigned s_need;
+        unsigned long long prefix = 0;
+        unsigned need = (unsigned)a.k;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            hist[tid] = 0;                                   // kSelThreads == 256
+            __syncthreads();
+            for (long long i = tid; i < a.n_db; i += kSelThreads) {
+                const unsigned long long key = ((unsigned long long)__ldcg(keys + i) << 32) | (unsigned)i;
+                if (key <= finite_max && (shift == 56 || (key >> (shift + 8)) == (prefix >> (shift + 8))))
+                    atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid == 0) {
+                unsigned acc = 0, b = 0;
+                for (; b < 255; ++b) {
+                    if (acc + hist[b] >= need) break;
+                    acc += hist[b];
+                }
+                s_prefix = prefix | ((unsigned long long)b << shift);
+                s_need = need - acc;                         // fewer than k finite keys: ends on the largest one
+            }
+            __syncthreads();
+            prefix = s_prefix;
+            need = s_need;
+        }
+        if (tid == 0) s_count = 0;
+        for (int i = tid; i < kSelCap; i += kSelThreads) sel[i] = ~0ull;
+        __syncthreads();
+        for (long long i = tid; i < a.n_db; i += kSelThreads) {
+            const unsigned long long key = ((unsigned long long)__ldcg(keys + i) << 32) | (unsigned)i;
+            if (key <= prefix && key <= finite_max) {
+                const int pos = atomicAdd(&s_count, 1);
+                if (pos < kSelCap) sel[pos] = key;
+            }
+        }
+        __syncthreads();
+        n_have = s_count < kSelCap ? s_count : kSelCap;
+    } else {
+        for (int i = tid; i < kSelCap; i += kSelThreads)
+            sel[i] = i < n_cand ? __ldcg(a.cand + (long long)q * kSelCap + i) : ~0ull;
+        __syncthreads();
     }
-    for (int i = tid; i < kSelCap; i += kSelThreads)
-        sel[i] = i < n_cand ? __ldcg(a.cand + (long long)q * kSelCap + i) : ~0ull;
-    __syncthreads();
     unsigned n_sort = 32;
-    while ((int)n_sort < n_cand) n_sort <<= 1;
+    while ((int)n_sort < n_have) n_sort <<= 1;
     bitonic_sort_keys<kSelThreads>(sel, n_sort);
     int valid = 0;                                          // finite candidates among the first k
     for (int i = tid; i < a.k; i += kSelThreads) {
-        const bool ok = i < n_cand && (unsigned)(sel[i] >> 32) < kInf;
+        const bool ok = i < n_have && (unsigned)(sel[i] >> 32) < kInf;
         a.top_idx[(long long)q * a.k + i] = ok ? (long long)(unsigned)(sel[i] & 0xffffffffull) : -1;
         a.top_dist[(long long)q * a.k + i] = ok ? __uint_as_float((unsigned)(sel[i] >> 32)) : INFINITY;
         valid += ok;
@@ -410,11 +463,6 @@ topk_kernel(const __grid_constant__ TopkArgs a) {
     __shared__ unsigned s_total, s_prefix, s_need, s_nvalid, s_eq_total, s_fill;
     __shared__ unsigned long long sel[kTopThreads];
     const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    if (a.only_if) {                     // fallback launch after select_kernel: usually nothing to do
-        if (a.only_if[4 * q + 2] == 0) return;
-        __syncthreads();
-        if (tid == 0) a.only_if[4 * q + 2] = 0;
-    }
     const unsigned* keys = reinterpret_cast<const unsigned*>(a.distances + (long long)q * a.n_db);
     const unsigned kInf = 0x7f800000u;
     const long long n_round = (a.n_db + kTopThreads - 1) / kTopThreads * kTopThreads;
@@ -613,7 +661,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
         // one grid for every group of queries (sized for the largest group), so that the rows of
         // warp minima have one length
         const int q_max = n_queries < kMaxQueries ? n_queries : kMaxQueries;
-        const size_t smem_max = (size_t)(q_max + kRWarps * kRowStages) * per * 32 * 4;
+        const size_t smem_max = (size_t)(q_max + kRWarps * (kRowStages + 1)) * per * 32 * 4;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return record_cuda(e);
         int per_sm = 0;
@@ -637,7 +685,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             a.n_db = n_db;
             a.n_bins = n_bins;
             a.eps = epsilon;
-            const size_t smem = (size_t)(a.n_queries + kRWarps * kRowStages) * per * 32 * 4;
+            const size_t smem = (size_t)(a.n_queries + kRWarps * (kRowStages + 1)) * per * 32 * 4;
             kern<<<(int)grid, kRThreads, smem, s>>>(a);
             e = cudaGetLastError();
             if (e != cudaSuccess) return record_cuda(e);
@@ -651,7 +699,6 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
         t.top_idx = (long long*)d_top_idx;
         t.top_dist = d_top_dist;
         t.top_count = d_top_count;
-        t.only_if = nullptr;
         if (fused_select) {
             SelectArgs sa;
             sa.distances = d_distances;
@@ -667,9 +714,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             long long per_q = (n_db + 4 * kSelThreads - 1) / (4 * kSelThreads);      // ~1024 rows per CTA
             const int ctas = (int)(per_q < 1 ? 1 : per_q > kSelCtas ? kSelCtas : per_q);
             select_kernel<<<dim3(ctas, n_queries), kSelThreads, 0, s>>>(sa);
-            cudaError_t e = cudaGetLastError();
-            if (e != cudaSuccess) return record_cuda(e);
-            t.only_if = counters;           // runs only for queries whose candidates overflowed
+            return record_cuda(cudaGetLastError());
         }
         topk_kernel<<<n_queries, kTopThreads, 0, s>>>(t);
         return record_cuda(cudaGetLastError());

@@ -176,6 +176,46 @@ def test_massive_ties_take_the_radix_path():
     assert idx[0].cpu().tolist() == [3003, 3006, 3000, 3002, 3005, 0, 1, 2, 3, 4, 5, 6]
 
 
+def test_candidate_overflow_takes_the_exact_radix_select(tmp_path):
+    """The many-CTA selection (k <= 128) keeps at most 1024 candidates; when more keys lie under
+    its bound, the last CTA runs an exact radix select over the 64-bit (distance, row) keys. The
+    tuning build has a 128-entry candidate list, which k = 100 .. 128 overflow on ordinary data."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from neural_spectral_codec_b200 import _lib
+    code = f"""
+import sys, numpy as np, torch
+sys.path.insert(0, {ROOT!r})
+sys.path.insert(0, {os.path.join(ROOT, "tests")!r})
+from neural_spectral_codec_b200.retrieval import WassersteinRetriever
+from oracle import retrieval_oracle as ro
+from test_gpu_retrieval import check_topk
+rng = np.random.default_rng(9)
+db = rng.gamma(0.5, 1.0, (30000, 800)).astype(np.float32)
+db /= db.sum(1, keepdims=True)
+db[100:140] = db[7]                                  # exact ties around the front
+qs = db[[7, 500, 29999]] + (0.1 * rng.random((3, 800)) / 800).astype(np.float32)
+xyz = np.stack([np.arange(len(db)) * 1.0, np.zeros(len(db)), np.zeros(len(db))], 1)
+r = WassersteinRetriever(device="cuda")
+r.add_to_database(db, positions=xyz)
+for k in (128, 100, 25, 1):
+    idx, top, cnt = r.query_batch(qs, top_k=k)
+    for i in range(3):
+        ref = ro.wasserstein_distance_batch(torch.from_numpy(qs[i]), torch.from_numpy(db)).numpy()
+        check_topk(idx[i].cpu().numpy(), top[i].cpu().numpy(), ref, k)
+# the spatial filter leaves 50 rows: fewer finite keys than k
+idx, top, cnt = r.query_batch(qs[:1], top_k=128, query_positions=xyz[7:8], spatial_filter_distance=29950.0)
+n_valid = int((np.abs(np.arange(len(db)) - 7) >= 29950.0).sum())
+assert cnt.item() == n_valid and (idx[0, n_valid:] == -1).all()
+assert (np.abs(idx[0, :n_valid].cpu().numpy() - 7) >= 29950).all()
+print("same")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                       env=dict(os.environ, NSC_LIB=_lib.TUNE_LIB_PATH), timeout=600)
+    assert r.returncode == 0 and "same" in r.stdout, r.stderr[-3000:]
+
+
 def test_gathered_encoder_output_feeds_the_retriever():
     """End of the path: descriptors from the fused encode kernel land in the database and the
     scan retrieves itself."""
