@@ -94,7 +94,12 @@ void nsc_default_params(nsc_params* p);
  * function serves non-Python callers and is tested equal to it. h_lut has NSC_N_FREQS ints. */
 int nsc_freq_to_bin(float alpha, const nsc_params* p, int32_t* h_lut);
 
-/* Device workspace needed by nsc_encode_batch / nsc_project_batch (a work counter). */
+/* Device workspace of nsc_encode_batch / nsc_encode_batch_peers / nsc_project_batch. 256 bytes (the
+ * work counter) are enough for every call and smaller workspaces are refused; the RECOMMENDED size
+ * returned here (a few MB) also holds one key image per scan of the grid's last, partial wave,
+ * which lets a batch whose last wave fills at most half of the SMs split those scans over all
+ * of them (+5 % on 600 scans). The result does not depend on the workspace size. Contents need
+ * no initialisation. */
 size_t nsc_workspace_bytes(int n_scans, const nsc_params* p);
 
 /* Replaces a loop of SpectralEncoder.encode_points (spectral_encoder.py:206-229; callers

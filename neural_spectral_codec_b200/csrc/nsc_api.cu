@@ -48,9 +48,9 @@ int nsc_encode_batch(const float* d_points, int point_stride, const int64_t* d_o
     if (st != NSC_OK) return st;
     if (n_scans == 0) return NSC_OK;
     if (!d_out) return NSC_ERR_NULL_POINTER;
-    if (!d_workspace || workspace_bytes < workspace_bytes_for(n_scans, dp.E)) return NSC_ERR_WORKSPACE;
+    if (!d_workspace || workspace_bytes < workspace_bytes_min()) return NSC_ERR_WORKSPACE;
     return launch_encode(d_points, point_stride, (const long long*)d_offsets, point_origin, n_scans,
-                         dp, d_out, nullptr, 0, nullptr, 0, 0, (unsigned*)d_workspace,
+                         dp, d_out, nullptr, 0, nullptr, 0, 0, (unsigned*)d_workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }
 
@@ -68,10 +68,10 @@ int nsc_encode_batch_peers(const float* d_points, int point_stride, const int64_
     for (int i = 0; i < n_peers; ++i)
         if (!h_peer_db[i]) return NSC_ERR_NULL_POINTER;
     if (n_scans == 0) return NSC_OK;
-    if (!d_workspace || workspace_bytes < workspace_bytes_for(n_scans, dp.E)) return NSC_ERR_WORKSPACE;
+    if (!d_workspace || workspace_bytes < workspace_bytes_min()) return NSC_ERR_WORKSPACE;
     return launch_encode(d_points, point_stride, (const long long*)d_offsets, point_origin, n_scans,
                          dp, nullptr, nullptr, 0, h_peer_db, n_peers, db_row0,
-                         (unsigned*)d_workspace, (cudaStream_t)stream);
+                         (unsigned*)d_workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 namespace {
@@ -123,9 +123,9 @@ int nsc_project_batch(const float* d_points, int point_stride, const int64_t* d_
     if (stage != NSC_STAGE_PROJECTED && stage != NSC_STAGE_INTERPOLATED) return NSC_ERR_BAD_PARAMS;
     if (n_scans == 0) return NSC_OK;
     if (!d_images) return NSC_ERR_NULL_POINTER;
-    if (!d_workspace || workspace_bytes < workspace_bytes_for(n_scans, dp.E)) return NSC_ERR_WORKSPACE;
+    if (!d_workspace || workspace_bytes < workspace_bytes_min()) return NSC_ERR_WORKSPACE;
     return launch_encode(d_points, point_stride, (const long long*)d_offsets, point_origin, n_scans,
-                         dp, nullptr, d_images, stage, nullptr, 0, 0, (unsigned*)d_workspace,
+                         dp, nullptr, d_images, stage, nullptr, 0, 0, (unsigned*)d_workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }
 
@@ -279,7 +279,7 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
             break;
         }
         st = launch_encode(s.d_points, point_stride, s.d_offsets, p0, ns, dp, s.d_out, nullptr, 0,
-                           nullptr, 0, 0, s.d_ws, s.stream);
+                           nullptr, 0, 0, s.d_ws, 256, s.stream);
         if (st != NSC_OK) break;
         if ((e = cudaMemcpyAsync(h_out + (size_t)first * D, s.d_out, (size_t)ns * D * 4,
                                  cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess ||
@@ -393,7 +393,7 @@ int nsc_pipeline_encode_scans(nsc_pipeline* pl, const float* const* h_scans, con
             break;
         }
         st = launch_encode(s.d_points, point_stride, s.d_offsets, 0, ns, dp, s.d_out, nullptr, 0, nullptr, 0,
-                           0, s.d_ws, s.stream);
+                           0, s.d_ws, 256, s.stream);
         if (st != NSC_OK) break;
         if ((e = cudaMemcpyAsync(s.h_out, s.d_out, (size_t)ns * D * 4, cudaMemcpyDeviceToHost, s.stream)) != cudaSuccess ||
             (e = cudaEventRecord(s.done, s.stream)) != cudaSuccess) {
@@ -456,7 +456,7 @@ int nsc_pipeline_encode_scan(nsc_pipeline* pl, const float* h_points, int point_
             cudaSuccess)
             return fail(e);
     }
-    st = launch_encode(s.d_points, point_stride, s.d_offsets, 0, 1, dp, d_out, nullptr, 0, nullptr, 0, 0, s.d_ws, cs);
+    st = launch_encode(s.d_points, point_stride, s.d_offsets, 0, 1, dp, d_out, nullptr, 0, nullptr, 0, 0, s.d_ws, 256, cs);
     if (st == NSC_OK) {
         if ((e = cudaEventRecord(s.done, cs)) != cudaSuccess) return fail(e);
         s.busy = true;

@@ -40,6 +40,11 @@ struct EncodeArgs {
     int stage;
     unsigned* counter;
     PeerOut peers;
+    // warp-specialised kernel: the last n_scans - n_whole scans are handed out in `parts` pieces
+    // each, so that the final, partial wave of the grid is spread over all CTAs (see launch_encode)
+    int n_whole, parts, n_units;
+    unsigned* part_arrive;       // one counter per split scan (zero before the launch)
+    unsigned* part_image;        // one E x 361 key image per split scan (0xffffffff before the launch)
 };
 
 // How the point pass is fed from HBM.
@@ -512,7 +517,7 @@ struct WsLayout {
         src_off = take(rows * 4);
         red_off = take(kWarps * 8 + 16);
         bins_off = take(NSC_MAX_BINS + 3);
-        mail_off = take(4 * 16 + 16);                    // 4 entries + tail_done
+        mail_off = take(4 * 16 + 16);                    // 4 entries + tail_done + the arrival ticket of a split scan
         mbar_off = take((2 * kWsDepth + 4) * 8);
         total = o;
     }
@@ -543,19 +548,29 @@ __device__ __forceinline__ void ws_producer_role(const EncodeArgs& a, unsigned c
     const WsBars bars(smem_u32(smem + L.mbar_off));
     const uint32_t ring = smem_u32(smem + L.ring_off);
     const float4* p4 = reinterpret_cast<const float4*>(a.points);
-    int scan = blockIdx.x;
+    int unit = blockIdx.x;
     int next = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
     const uint64_t pol = l2_policy_evict_first();
     const bool hint = NSC_L2_HINTS != 0 && a.peers.n == 0;
     uint32_t slot = 0, phase = 0;                     // phase = (stage counter / kWsDepth) & 1
     bool wrapped = false;
     for (int k = 0;; ++k) {
-        int n = 0;
+        int n = 0, scan = a.n_scans;
         const float4* src = p4;
-        if (scan < a.n_scans) {
+        if (unit < a.n_units) {
+            // units 0 .. n_whole-1 are whole scans; the rest are the `parts` pieces of the last scans
+            const int j = unit - a.n_whole;
+            scan = j < 0 ? unit : a.n_whole + j / a.parts;
             const long long o0 = a.offsets[scan];
-            n = (int)(a.offsets[scan + 1] - o0);
-            src += o0 - a.origin;
+            const long long n_tot = a.offsets[scan + 1] - o0;
+            long long lo = 0, hi = n_tot;
+            if (j >= 0) {
+                const int part = j % a.parts;
+                lo = n_tot * part / a.parts;
+                hi = n_tot * (part + 1) / a.parts;
+            }
+            n = (int)(hi - lo);
+            src += o0 - a.origin + lo;
         }
         while (*tail_done < k - 3) { }                // entry k & 3 is free: scan k - 4 is finished
         volatile int* e = mail + 4 * (k & 3);
@@ -572,8 +587,8 @@ __device__ __forceinline__ void ws_producer_role(const EncodeArgs& a, unsigned c
             else bulk_copy_g2s(ring + slot * kWsSlotBytes, src + base, bytes, bars.slot_full(slot));
             if (++slot == kWsDepth) { slot = 0; phase ^= 1; wrapped = true; }
         }
-        scan = next;
-        if (scan < a.n_scans) next = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
+        unit = next;
+        if (unit < a.n_units) next = (int)gridDim.x + (int)atomicAdd(a.counter, 1u);
     }
 }
 
@@ -654,6 +669,27 @@ __device__ __forceinline__ void ws_tail_role(const EncodeArgs& a, const DevicePa
             __syncwarp();
             if ((gt & 31) == 0) mbar_arrive(bars.img_empty(b));
         };
+        if (scan >= a.n_whole) {
+            // One piece of a split scan: min-merge this image into the scan's image in global
+            // memory; the CTA that brings the last piece takes the merged image back and runs the
+            // tail, the others hand their image back and move on.
+            unsigned* g = a.part_image + (size_t)(scan - a.n_whole) * L.img_words;
+            for (int i = gt; i < L.img_words; i += G::kSize)
+                if (img[i] != kInfBits) atomicMin(g + i, img[i]);
+            __threadfence();
+            G::sync();
+            if (gt == 0) mail[17] = (int)atomicAdd(a.part_arrive + (scan - a.n_whole), 1u);
+            G::sync();
+            if (mail[17] != a.parts - 1) {
+                release();
+                G::sync();
+                if (gt == 0) mail[16] = k + 1;            // tail_done
+                continue;
+            }
+            __threadfence();
+            for (int i = gt; i < L.img_words; i += G::kSize) img[i] = __ldcg(g + i);
+            G::sync();
+        }
 #ifdef NSC_EXP_SKIP_TAIL
         release();      // measurement-only build: no tail at all (descriptors are not written)
 #elif defined(NSC_EXP_TAIL_PARTS)
@@ -946,16 +982,24 @@ int configure(K kernel, int smem, const DeviceInfo& di, int* blocks_per_sm) {
 
 }  // namespace
 
+// Workspace: [0, 256) work counter; [256, 256 + 4 * kMaxSplitScans) arrival counters and then one
+// E x 361 key image per split scan (launch_encode splits the scans of the last, partial wave of the
+// grid when the workspace has room for it; kMinWorkspace is enough for everything else).
+constexpr int kMaxSplitScans = 256;
+constexpr size_t kMinWorkspace = 256;
+static size_t split_workspace(int n_split, int E) {
+    return kMinWorkspace + (size_t)kMaxSplitScans * 4 + (size_t)n_split * E * kPitch * 4;
+}
 size_t workspace_bytes_for(int n_scans, int E) {
     (void)n_scans;
-    (void)E;
-    return 256;   // work counter (+ padding)
+    return split_workspace(kMaxSplitScans - 1, E);
 }
+size_t workspace_bytes_min() { return kMinWorkspace; }
 
 int launch_encode(const float* d_points, int stride, const long long* d_offsets, long long origin,
                   int n_scans, const DeviceParams& dp, float* d_out, float* d_img_out, int stage,
                   float* const* d_peer_out, int n_peers, long long peer_row0,
-                  unsigned* d_workspace, cudaStream_t stream) {
+                  unsigned* d_workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (n_scans == 0) return NSC_OK;
     DeviceInfo di;
     int st = device_info(&di);
@@ -972,12 +1016,17 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     a.peers.n = n_peers;
     a.peers.row0 = peer_row0;
     for (int i = 0; i < NSC_MAX_PEERS; ++i) a.peers.ptr[i] = i < n_peers ? d_peer_out[i] : nullptr;
+    a.n_whole = n_scans;
+    a.parts = 1;
+    a.n_units = n_scans;
+    a.part_arrive = nullptr;
+    a.part_image = nullptr;
 
     // Feed of the point pass (see enum Feed) and kernel choice. Product builds take no switches;
     // tuning builds (-DNSC_TUNING, csrc/Makefile VARIANT=tune) read NSC_FEED=ldg|cpasync|tma,
     // NSC_SPLIT=0 and NSC_WS=0 from the environment, once, for A/B runs and the bit-identity tests.
     int feed = kDefaultFeed;
-    bool split_allowed = true, ws_allowed = true;
+    bool split_allowed = true, ws_allowed = true, tail_split_allowed = true;
 #ifdef NSC_TUNING
     static const int feed_override = [] {
         const char* e = getenv("NSC_FEED");
@@ -987,6 +1036,8 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
     }();
     static const bool env_split = [] { const char* e = getenv("NSC_SPLIT"); return !(e && e[0] == '0'); }();
     static const bool env_ws = [] { const char* e = getenv("NSC_WS"); return !(e && e[0] == '0'); }();
+    static const bool env_ts = [] { const char* e = getenv("NSC_TAILSPLIT"); return !(e && e[0] == '0'); }();
+    tail_split_allowed = env_ts;
     if (feed_override >= 0) feed = feed_override;
     split_allowed = env_split;
     ws_allowed = env_ws && feed_override < 0;
@@ -1037,9 +1088,32 @@ int launch_encode(const float* d_points, int stride, const long long* d_offsets,
         kernel = poly ? encode_points_ws_kernel<kRowPoly> : encode_points_ws_kernel<kRowSearch>;
         st = configure(kernel, W.total, di, nullptr);
         if (st != NSC_OK) return st;
-        cudaError_t e = cudaMemsetAsync(d_workspace, 0, 2 * sizeof(unsigned), stream);
-        if (e != cudaSuccess) return record_cuda(e);
         const int grid = di.sms < n_scans ? di.sms : n_scans;
+        // The scans are handed out dynamically, one per CTA at a time, so the last R = n_scans mod
+        // grid of them keep only part of the GPU busy for a whole scan time. When R <= grid / 2 each
+        // of them is split into P = floor(grid / R) pieces (merged through a key image in global
+        // memory by the tail warps), one piece per CTA: that wave then lasts 1 / P of a scan time
+        // (600 scans: +5 %, profiles/r2s_ab_hdl64_600.txt). More pieces than CTAs do not pay: a
+        // piece streams faster than its tail -- the merge, and for the last piece the whole FFT --
+        // runs, and the tail warps become the bottleneck (4541 scans as 4 pieces each: -3 %).
+        const int R = n_scans > grid ? n_scans % grid : 0;
+        if (tail_split_allowed && R > 0 && 2 * R <= grid) {
+            int P = grid / R;
+            if (P > 8) P = 8;
+            if (workspace_bytes >= split_workspace(R, dp.E)) {
+                a.n_whole = n_scans - R;
+                a.parts = P;
+                a.n_units = a.n_whole + R * P;
+                a.part_arrive = d_workspace + kMinWorkspace / 4;
+                a.part_image = a.part_arrive + kMaxSplitScans;
+            }
+        }
+        cudaError_t e = cudaMemsetAsync(d_workspace, 0, a.parts > 1 ? kMinWorkspace + (size_t)kMaxSplitScans * 4 : 8, stream);
+        if (e != cudaSuccess) return record_cuda(e);
+        if (a.parts > 1) {
+            e = cudaMemsetAsync(a.part_image, 0xff, (size_t)R * dp.E * kPitch * 4, stream);
+            if (e != cudaSuccess) return record_cuda(e);
+        }
         kernel<<<grid, kWsThreads, W.total, stream>>>(a, dp);
         return record_cuda(cudaGetLastError());
     }

@@ -47,10 +47,11 @@ int record_cuda(cudaError_t e);
 int launch_encode(const float* d_points, int stride, const long long* d_offsets, long long origin,
                   int n_scans, const DeviceParams& dp, float* d_out, float* d_img_out, int stage,
                   float* const* d_peer_out, int n_peers, long long peer_row0,
-                  unsigned* d_workspace, cudaStream_t stream);
+                  unsigned* d_workspace, size_t workspace_bytes, cudaStream_t stream);
 int launch_encode_images(const float* d_images, int n_images, int rows, const DeviceParams& dp,
                          float* d_out, cudaStream_t stream);
 int launch_interpolate(const float* d_in, int n_images, int rows, int nearest, float* d_out, cudaStream_t stream);
-size_t workspace_bytes_for(int n_scans, int E);
+size_t workspace_bytes_for(int n_scans, int E);   // recommended: room to split the last wave's scans
+size_t workspace_bytes_min();                      // enough for every launch (no splitting)
 
 }  // namespace nsc

@@ -154,10 +154,10 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
     // the first rows are on their way while the query CDFs are built
 #pragma unroll
     for (int s = 0; s < kRowStages - 1; ++s) issue(r0 + s * n_warps, s);
-    // query CDFs (wasserstein.py:152-154,165), one warp per query, staged through the warp's
-    // slice of the area behind the rings
+    // query CDFs (wasserstein.py:152-154,165), one warp per query, staged through the ring slot
+    // the prologue above left free (its padding lanes stay zero)
     {
-        float* stage = smem + a.n_queries * padded + kRWarps * (kRowStages * padded) + warp * padded;
+        float* stage = ring + (kRowStages - 1) * padded;
         for (int q = warp; q < a.n_queries; q += kRWarps) {
             for (int e = lane; e < padded; e += 32) stage[e] = e < a.n_bins ? a.queries[(long long)q * a.n_bins + e] : 0.0f;
             __syncwarp();
@@ -661,7 +661,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
         // one grid for every group of queries (sized for the largest group), so that the rows of
         // warp minima have one length
         const int q_max = n_queries < kMaxQueries ? n_queries : kMaxQueries;
-        const size_t smem_max = (size_t)(q_max + kRWarps * (kRowStages + 1)) * per * 32 * 4;
+        const size_t smem_max = (size_t)(q_max + kRWarps * kRowStages) * per * 32 * 4;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return record_cuda(e);
         int per_sm = 0;
@@ -685,7 +685,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             a.n_db = n_db;
             a.n_bins = n_bins;
             a.eps = epsilon;
-            const size_t smem = (size_t)(a.n_queries + kRWarps * (kRowStages + 1)) * per * 32 * 4;
+            const size_t smem = (size_t)(a.n_queries + kRWarps * kRowStages) * per * 32 * 4;
             kern<<<(int)grid, kRThreads, smem, s>>>(a);
             e = cudaGetLastError();
             if (e != cudaSuccess) return record_cuda(e);

@@ -99,7 +99,8 @@ class ShardedEncoder:
             self._step = 0                    # steps enqueued
             self._complete = 0                # steps whose database is complete in stream order
             self.db = self._dbs[0]
-            self._ws = torch.empty(64, dtype=torch.int32, device=dev)
+            need = int(_lib.load().nsc_workspace_bytes(self.per, C.byref(encoder._params())))
+            self._ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=dev)
             self.local = None
 
     def _signal_wait(self, wait_value: int) -> None:

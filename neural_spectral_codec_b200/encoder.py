@@ -82,13 +82,13 @@ class RangeImageProjector:
         dev = points.device
         out = torch.empty((n_scans, self.n_elevation, self.n_azimuth), dtype=torch.float32, device=dev)
         p = self._params()
-        ws = torch.empty(64, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws = _workspace(dev, stream, p, n_scans)
             st = lib.nsc_project_batch(
                 points.data_ptr(), stride, offsets.data_ptr(), 0, n_scans, C.byref(p),
                 _lib.STAGE_INTERPOLATED if interpolate else _lib.STAGE_PROJECTED,
-                out.data_ptr(), ws.data_ptr(), ws.numel() * 4,
-                torch.cuda.current_stream(dev).cuda_stream)
+                out.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
         _lib.check(st, "nsc_project_batch")
         return out
 
@@ -124,6 +124,22 @@ class RangeImageProjector:
             return rng[0].cpu().numpy(), inten[0].cpu().numpy()
         img = self.project_batch(pts, offs)[0]
         return img.cpu().numpy(), None
+
+
+_WORKSPACES = {}
+
+
+def _workspace(dev: torch.device, stream: int, p: "_lib.NscParams", n_scans: int) -> torch.Tensor:
+    """Device workspace of the encode kernels (``nsc_workspace_bytes``: the work counter plus room
+    to split the scans of the grid's last wave), one per (device, stream): launches on one
+    stream are ordered, so they can share it."""
+    need = int(_lib.load().nsc_workspace_bytes(n_scans, C.byref(p)))
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() * 4 < need:
+        ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
 
 
 def _check_batch(points: torch.Tensor, offsets: torch.Tensor):
@@ -256,11 +272,12 @@ class SpectralEncoder(nn.Module):
             raise ValueError("out must be a contiguous float32 (B, output_dim) tensor on the same device")
         p = self._params()
         lut = self.freq_to_bin()
-        ws = torch.empty(64, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            ws = _workspace(dev, stream, p, n_scans)
             st = lib.nsc_encode_batch(points.data_ptr(), stride, offsets.data_ptr(), 0, n_scans,
                                       C.byref(p), lut.ctypes.data, out.data_ptr(), ws.data_ptr(),
-                                      ws.numel() * 4, torch.cuda.current_stream(dev).cuda_stream)
+                                      ws.numel() * 4, stream)
         _lib.check(st, "nsc_encode_batch")
         return out
 

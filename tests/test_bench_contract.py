@@ -35,12 +35,12 @@ def test_both_arms_describe_the_same_config():
     sys.path.insert(0, ROOT)
     import bench
     for gpus in (1, 8):
-        a = argparse.Namespace(scans=bench.N_SCANS, shape="hdl64", shuffle=False, gather="fused", gpus=gpus)
+        a = argparse.Namespace(scans=bench.N_SCANS, shape="hdl64", shuffle=False, gather="fused", gather_lag=0, gpus=gpus)
         assert bench.make_config(a, gpus) == bench.make_config(a, gpus)
         assert "model" not in bench.make_config(a, gpus) and "workload" in bench.make_config(a, gpus)
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                         "--warmup", "0", "--gpus", "8"], capture_output=True, text=True, timeout=600,
                        env=dict(os.environ, RANK="0", WORLD_SIZE="8"))
     d = json.loads(r.stdout.strip().splitlines()[-1])
-    a = argparse.Namespace(scans=bench.N_SCANS, shape="hdl64", shuffle=False, gather="fused", gpus=8)
+    a = argparse.Namespace(scans=bench.N_SCANS, shape="hdl64", shuffle=False, gather="fused", gather_lag=0, gpus=8)
     assert d["config"] == bench.make_config(a, 8) and d["n_gpus"] == 8
