@@ -112,7 +112,7 @@ struct QueryArgs {
     float eps;
 };
 
-constexpr int kRowStages = 3;   // CDF rows in flight per warp (cp.async ring)
+// CDF rows per warp ring (one fewer in flight): 4 when two CTAs per SM still fit, else 3
 
 __device__ __forceinline__ void cp_async4(float* dst, const float* src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
@@ -124,7 +124,7 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
 }
 
 // PER = elements per lane (n_bins <= 32 * PER); PER = 25 is the 800-D descriptor.
-template <int PER>
+template <int PER, int kRowStages>
 __global__ void __launch_bounds__(kRThreads)
 wasserstein_kernel(const __grid_constant__ QueryArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -654,15 +654,24 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
     if (n_db > 0) {
         void (*kern)(const QueryArgs) = nullptr;
         int per = (n_bins + 31) / 32;
-        if (per <= 8) { kern = wasserstein_kernel<8>; per = 8; }
-        else if (per <= 16) { kern = wasserstein_kernel<16>; per = 16; }
-        else if (per <= 25) { kern = wasserstein_kernel<25>; per = 25; }
-        else { kern = wasserstein_kernel<32>; per = 32; }
+        per = per <= 8 ? 8 : per <= 16 ? 16 : per <= 25 ? 25 : 32;
         // one grid for every group of queries (sized for the largest group), so that the rows of
         // warp minima have one length
         const int q_max = n_queries < kMaxQueries ? n_queries : kMaxQueries;
-        const size_t smem_max = (size_t)(q_max + kRWarps * kRowStages) * per * 32 * 4;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
+        int smem_optin = 0, dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e != cudaSuccess) return record_cuda(e);
+        auto smem_for = [&](int nq, int stages) { return (size_t)(nq + kRWarps * stages) * per * 32 * 4; };
+        const int stages = 2 * (smem_for(q_max, 4) + 1024) <= (size_t)smem_optin ? 4 : 3;   // keep two CTAs per SM
+        if (stages == 4)
+            kern = per == 8 ? wasserstein_kernel<8, 4> : per == 16 ? wasserstein_kernel<16, 4>
+                   : per == 25 ? wasserstein_kernel<25, 4> : wasserstein_kernel<32, 4>;
+        else
+            kern = per == 8 ? wasserstein_kernel<8, 3> : per == 16 ? wasserstein_kernel<16, 3>
+                   : per == 25 ? wasserstein_kernel<25, 3> : wasserstein_kernel<32, 3>;
+        const size_t smem_max = smem_for(q_max, stages);
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
         if (e != cudaSuccess) return record_cuda(e);
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRThreads, smem_max);
@@ -685,8 +694,7 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             a.n_db = n_db;
             a.n_bins = n_bins;
             a.eps = epsilon;
-            const size_t smem = (size_t)(a.n_queries + kRWarps * kRowStages) * per * 32 * 4;
-            kern<<<(int)grid, kRThreads, smem, s>>>(a);
+            kern<<<(int)grid, kRThreads, smem_for(a.n_queries, stages), s>>>(a);
             e = cudaGetLastError();
             if (e != cudaSuccess) return record_cuda(e);
         }
