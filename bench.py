@@ -748,6 +748,93 @@ def run_retrieval(args):
     emit(line)
 
 
+# ----------------------------------------------------------------------------- keyframe gate (secondary)
+def run_keyframe(args):
+    """Secondary workload: voxel-IoU of (last keyframe, scan) pairs, the
+    expensive criterion of the reference's keyframe gate (pose_utils.py:323-389), 5000 + 5000 points
+    per pair as after its subsample. Kernel time with device-resident pairs, the public batched call
+    from host arrays, and the reference's own compute_overlap on one core."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+
+    from neural_spectral_codec_b200 import _lib, keyframe as kf, synth
+    dev = torch.device("cuda")
+    lib = _lib.load()
+    n_pairs = args.pairs
+    shape = synth.SensorShape("kf", 32, -24.8, 2.0, 400)
+    rng = np.random.default_rng(0)
+    clouds = [synth.make_scan(shape, 300 + i).numpy() for i in range(16)]
+    pairs = []
+    for i in range(n_pairs):
+        a, b = clouds[i % 16], clouds[(i + 1 + i // 16) % 16]
+        pa = a[rng.choice(len(a), 5000, replace=False)]
+        pb = b[rng.choice(len(b), 5000, replace=False)]
+        T = np.eye(4)
+        ang = 0.01 * (i % 7)
+        T[:2, :2] = [[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]]
+        T[0, 3] = 0.05 * (i % 5)
+        pairs.append((pa, pb, T))
+    iou = kf.compute_overlap_batch(pairs)                       # warm-up + result
+    t0 = time.perf_counter()
+    for _ in range(3):
+        kf.compute_overlap_batch(pairs)
+    api_s = (time.perf_counter() - t0) / 3
+    # kernel alone, inputs resident
+    pts = torch.from_numpy(np.concatenate([np.concatenate([p[0], p[1]]) for p in pairs])).to(dev)
+    offs = torch.arange(0, 2 * n_pairs + 1, dtype=torch.int64, device=dev) * 5000
+    Ts = torch.from_numpy(np.stack([p[2] for p in pairs])).to(dev)
+    cnt = torch.empty((n_pairs, 3), dtype=torch.int32, device=dev)
+    out = torch.empty((n_pairs,), dtype=torch.float64, device=dev)
+    total = 10000 * n_pairs
+    ws = torch.empty(int(lib.nsc_voxel_overlap_workspace_bytes(total, 10000, n_pairs)) // 4 + 1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def launch():
+        st = lib.nsc_voxel_overlap_batch(pts.data_ptr(), 4, 0, offs.data_ptr(), total, 10000, Ts.data_ptr(), n_pairs, 0.2,
+                                         cnt.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel() * 4, stream)
+        assert st == 0
+    for _ in range(3):
+        launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    assert np.array_equal(out.cpu().numpy(), iou)
+    peak, _ = hbm_peak()
+    line = {"metric": "keyframe_overlap_pairs_per_sec", "value": n_pairs / (ms * 1e-3), "unit": "pairs/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 transform / f32 voxels / int32 sets", "data": "synthetic",
+            "config": {"workload": f"voxel IoU of {n_pairs} cloud pairs of 5000 + 5000 xyzi points, 0.2 m voxels"},
+            "roofline": {"bound": "latency (shared-memory hash set: one atomicCAS chain per point)",
+                         "achieved": 16.0 * total / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": 16.0 * total / (ms * 1e-3) / 1e9 / peak, "traffic": None},
+            "e2e": {"value": n_pairs / api_s, "unit": "pairs/s", "api": "keyframe.compute_overlap_batch(host arrays)",
+                    "h2d_bytes_per_step": 16 * total, "d2h_bytes_per_step": 8 * n_pairs},
+            "gpu_launches": args.steps}
+    if not args.no_cpu:
+        src = reference_src()
+        kind = "reference" if src else "port"
+        if src:
+            sys.path.insert(0, src)
+            from data.pose_utils import compute_overlap as ref_overlap
+        else:
+            from oracle.keyframe_oracle import compute_overlap as ref_overlap
+        n = min(n_pairs, 24)
+        t0 = time.perf_counter()
+        got = [ref_overlap(p[0], p[1], p[2], voxel_size=0.2) for p in pairs[:n]]
+        cpu_s = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "pairs/s", "cores": 1, "kind": kind,
+                                "sample": f"{n} pairs, compute_overlap (pose_utils.py:323-389), one process"}
+        line["checks"] = {"equal_to_cpu": bool(np.array_equal(np.array(got), iou[:n]))}
+    emit(line)
+
+
 def emit(line: dict) -> None:
     """The one JSON line goes to the REAL stdout; everything else a library prints to fd 1
     (e.g. NCCL's version banner) was redirected to stderr in main()."""
@@ -781,8 +868,10 @@ def main():
     ap.add_argument("--shape", default="hdl64", choices=sorted(SHAPE_DESC),
                     help="sensor shape of the synthetic scans (BASELINE.json configs 2-4; default = the metric's config)")
     ap.add_argument("--shuffle", action="store_true", help="random point order inside each scan")
-    ap.add_argument("--workload", default="encode", choices=["encode", "retrieval"],
-                    help="encode = the BASELINE.json metric (default); retrieval = secondary stage-1 retrieval line")
+    ap.add_argument("--workload", default="encode", choices=["encode", "retrieval", "keyframe"],
+                    help="encode = the BASELINE.json metric (default); retrieval / keyframe = secondary lines "
+                         "for the stage-1 retrieval and the keyframe-gate voxel IoU")
+    ap.add_argument("--pairs", type=int, default=512, help="keyframe: cloud pairs per launch")
     ap.add_argument("--db", type=int, default=100000, help="retrieval: database rows")
     ap.add_argument("--queries", type=int, default=8, help="retrieval: queries per call")
     ap.add_argument("--topk", type=int, default=10, help="retrieval: K")
@@ -793,6 +882,8 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.workload == "retrieval":
         run_retrieval(args)
+    elif args.workload == "keyframe":
+        run_keyframe(args)
     else:
         run_gpu_arm(args)
 
