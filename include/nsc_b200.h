@@ -64,7 +64,7 @@ typedef enum nsc_status {
 typedef struct nsc_params {
     int32_t struct_size;
     int32_t n_elevation;        /* rows of the projected image, 1..NSC_MAX_ELEVATION       */
-    int32_t n_azimuth;          /* must be NSC_N_AZIMUTH                                    */
+    int32_t n_azimuth;          /* NSC_N_AZIMUTH for the fused kernels; nsc_anywidth_* take others */
     int32_t n_bins;             /* histogram bins per row, 1..NSC_MAX_BINS                  */
     int32_t target_rows;        /* target_elevation_bins; rows are average-pooled to this   */
     int32_t interpolate_empty;  /* 1 = fill empty pixels before the FFT (reference default) */
@@ -181,6 +181,27 @@ int nsc_encode_range_images(const float* d_images, int n_images, int rows, const
 #define NSC_INTERP_NEAREST 1
 int nsc_interpolate_range_images(const float* d_images_in, int n_images, int rows, int method,
                                  float* d_images_out, void* stream);
+
+/* ---- image widths other than 360 columns ----------------------------------------------------
+ * The reference accepts any n_azimuth (spectral_encoder.py:35-47, range_image.py:102-127); every
+ * shipped config uses 360, which the entry points above are specialised to (they refuse other
+ * widths with NSC_ERR_BAD_PARAMS). These two cover 2 <= n_azimuth <= 4096 with one general kernel
+ * (the reference's own operation order for the projection, a direct float64 DFT per row): same
+ * results to the same tolerances, ~0.1-0.3 ms per scan instead of ~0.3 us. h_lut has
+ * n_azimuth / 2 + 1 entries. Workspace: nsc_anywidth_workspace_bytes(n, rows, p).
+ *   nsc_anywidth_points  encode_points / project [+ interpolate_range_image] for n_scans scans:
+ *       d_out (descriptors, float32[n_scans * target_rows * n_bins]) and / or d_images
+ *       (float32[n_scans * n_elevation * n_azimuth], the image named by `stage`); either may be NULL
+ *   nsc_anywidth_images  forward / encode_range_image (interp_method = -1: no interpolation, as the
+ *       reference's forward) and interpolate_range_image (d_out NULL, d_images_out set,
+ *       interp_method NSC_INTERP_LINEAR | NSC_INTERP_NEAREST) on images already on the device */
+size_t nsc_anywidth_workspace_bytes(int n, int rows, const nsc_params* p);
+int nsc_anywidth_points(const float* d_points, int point_stride, const int64_t* d_offsets, int64_t point_origin,
+                        int n_scans, const nsc_params* p, const int32_t* h_lut, float* d_out, float* d_images,
+                        int stage, void* d_workspace, size_t workspace_bytes, void* stream);
+int nsc_anywidth_images(const float* d_images_in, int n_images, int rows, const nsc_params* p, const int32_t* h_lut,
+                        int interp_method, float* d_out, float* d_images_out, void* d_workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* ---- host-buffer pipeline (the end-to-end call: H2D, encode, D2H inside) -------------- */
 typedef struct nsc_pipeline nsc_pipeline;

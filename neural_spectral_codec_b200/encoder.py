@@ -48,8 +48,8 @@ class RangeImageProjector:
     def __init__(self, n_elevation: int = 64, n_azimuth: int = 360,
                  elevation_range: Tuple[float, float] = (-24.8, 2.0),
                  max_range: float = 80.0, min_range: float = 1.0, device=None):
-        if n_azimuth != _lib.N_AZIMUTH:
-            raise ValueError("the CUDA encoder is specialised to n_azimuth = 360")
+        if not 2 <= int(n_azimuth) <= 4096:
+            raise ValueError("n_azimuth must be in [2, 4096]")
         self.n_elevation = n_elevation
         self.n_azimuth = n_azimuth
         self.max_range = max_range
@@ -71,6 +71,7 @@ class RangeImageProjector:
         p = _lib.NscParams()
         _lib.load().nsc_default_params(C.byref(p))
         self._fill_params(p)
+        p.n_bins, p.target_rows = 1, 1        # the projector has no spectrum; keeps any width valid
         return p
 
     def project_batch(self, points: torch.Tensor, offsets: torch.Tensor,
@@ -82,6 +83,10 @@ class RangeImageProjector:
         dev = points.device
         out = torch.empty((n_scans, self.n_elevation, self.n_azimuth), dtype=torch.float32, device=dev)
         p = self._params()
+        if self.n_azimuth != _lib.N_AZIMUTH:
+            _anywidth_points(points, offsets, n_scans, stride, p, None, None, out,
+                             _lib.STAGE_INTERPOLATED if interpolate else _lib.STAGE_PROJECTED)
+            return out
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws = _workspace(dev, stream, p, n_scans)
@@ -99,6 +104,8 @@ class RangeImageProjector:
         points, offsets, n_scans, stride = _check_batch(points, offsets)
         if stride != 4:
             raise ValueError("the intensity image needs (N, 4) points")
+        if self.n_azimuth != _lib.N_AZIMUTH:
+            raise NotImplementedError("the intensity image (off the encoding path) is built for n_azimuth = 360 only")
         dev = points.device
         shape = (n_scans, self.n_elevation, self.n_azimuth)
         rng = torch.empty(shape, dtype=torch.float32, device=dev)
@@ -140,6 +147,44 @@ def _workspace(dev: torch.device, stream: int, p: "_lib.NscParams", n_scans: int
         ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=dev)
         _WORKSPACES[key] = ws
     return ws
+
+
+def _anywidth_workspace(dev: torch.device, stream: int, p: "_lib.NscParams", n: int, rows: int) -> torch.Tensor:
+    need = int(_lib.load().nsc_anywidth_workspace_bytes(n, rows, C.byref(p)))
+    if need == 0:
+        raise ValueError("encoder geometry outside the supported envelope (rows <= 64, 2 <= n_azimuth <= 4096, "
+                         "n_bins <= n_azimuth // 2 + 1)")
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, "anywidth")
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() * 4 < need:
+        ws = torch.empty((need + 3) // 4, dtype=torch.int32, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _anywidth_points(points, offsets, n_scans, stride, p, lut, out, images, stage):
+    """Widths other than 360: the general kernel (``nsc_anywidth_points``)."""
+    dev = points.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _anywidth_workspace(dev, stream, p, n_scans, p.n_elevation)
+        st = _lib.load().nsc_anywidth_points(
+            points.data_ptr(), stride, offsets.data_ptr(), 0, n_scans, C.byref(p),
+            lut.ctypes.data if lut is not None else None, out.data_ptr() if out is not None else None,
+            images.data_ptr() if images is not None else None, stage, ws.data_ptr(), ws.numel() * 4, stream)
+    _lib.check(st, "nsc_anywidth_points")
+
+
+def _anywidth_images(x, p, lut, method, out, images_out):
+    dev = x.device
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        ws = _anywidth_workspace(dev, stream, p, x.shape[0], x.shape[1])
+        st = _lib.load().nsc_anywidth_images(
+            x.data_ptr(), x.shape[0], x.shape[1], C.byref(p), lut.ctypes.data if lut is not None else None, method,
+            out.data_ptr() if out is not None else None, images_out.data_ptr() if images_out is not None else None,
+            ws.data_ptr(), ws.numel() * 4, stream)
+    _lib.check(st, "nsc_anywidth_images")
 
 
 def _check_batch(points: torch.Tensor, offsets: torch.Tensor):
@@ -272,6 +317,9 @@ class SpectralEncoder(nn.Module):
             raise ValueError("out must be a contiguous float32 (B, output_dim) tensor on the same device")
         p = self._params()
         lut = self.freq_to_bin()
+        if self.n_azimuth != _lib.N_AZIMUTH:
+            _anywidth_points(points, offsets, n_scans, stride, p, lut, out, None, _lib.STAGE_INTERPOLATED)
+            return out
         with torch.cuda.device(dev):
             stream = torch.cuda.current_stream(dev).cuda_stream
             ws = _workspace(dev, stream, p, n_scans)
@@ -292,8 +340,10 @@ class SpectralEncoder(nn.Module):
             if pts.shape[1] > 4:
                 pts = pts[:, :3]
             offs = torch.tensor([0, pts.shape[0]], dtype=torch.int64).to(dev)
-        else:
+        elif self.n_azimuth == _lib.N_AZIMUTH:
             return self._encode_host_scan(_as_f32_points(points), dev)
+        else:
+            pts, offs = _host_scan_to_device(points, dev)
         return self.encode_points_batch(pts, offs)[0]
 
     def _encode_host_scan(self, a: np.ndarray, dev: torch.device) -> torch.Tensor:
@@ -356,6 +406,11 @@ class SpectralEncoder(nn.Module):
             raise ValueError("out must be contiguous float32 (B, output_dim)")
         if n_scans == 0:
             return out
+        if self.n_azimuth != _lib.N_AZIMUTH:     # other widths: the general kernel, one device batch
+            host = pts if arrs is None else (np.concatenate(arrs) if len(arrs) else np.zeros((0, 4), np.float32))
+            d = self.encode_points_batch(torch.from_numpy(np.ascontiguousarray(host)).to(dev), torch.from_numpy(offs))
+            out[...] = d.cpu().numpy()
+            return out
         biggest = int(np.diff(offs).max())
         chunk = max(int(max_chunk_points), biggest)
         key = (dev.index if dev.index is not None else torch.cuda.current_device(), chunk, n_buffers)
@@ -400,7 +455,7 @@ class SpectralEncoder(nn.Module):
         lib = _lib.load()
         dev = self._cuda_device("forward")
         if x.dim() != 3 or x.shape[2] != self.n_azimuth:
-            raise ValueError("expected (batch, n_elevation, 360) range images")
+            raise ValueError("expected (batch, n_elevation, n_azimuth) range images")
         if x.requires_grad and torch.is_grad_enabled():
             # the reference's forward is differentiable w.r.t. the range image; this kernel is
             # forward-only (no caller of the reference backpropagates through the encoder:
@@ -411,6 +466,10 @@ class SpectralEncoder(nn.Module):
         out = torch.empty((x.shape[0], self.output_dim), dtype=torch.float32, device=dev)
         p = self._params()
         lut = self.freq_to_bin()
+        if self.n_azimuth != _lib.N_AZIMUTH:
+            if x.shape[0]:
+                _anywidth_images(x, p, lut, -1, out, None)
+            return out
         with torch.cuda.device(dev):
             st = lib.nsc_encode_range_images(x.data_ptr(), x.shape[0], x.shape[1], C.byref(p),
                                              lut.ctypes.data, out.data_ptr(),
@@ -429,7 +488,7 @@ class SpectralEncoder(nn.Module):
 def interpolate_range_image(range_image: Union[np.ndarray, torch.Tensor], method: str = "linear",
                             device="cuda"):
     """``interpolate_range_image`` of the reference (range_image.py:15-89) on the GPU. Accepts a
-    ``(rows, 360)`` image or a ``(B, rows, 360)`` batch; numpy in -> numpy out."""
+    ``(rows, width)`` image or a ``(B, rows, width)`` batch; numpy in -> numpy out."""
     if method not in ("linear", "nearest"):
         # the reference silently leaves the holes of partly filled rows for any other string
         raise ValueError("method must be 'linear' or 'nearest'")
@@ -443,6 +502,15 @@ def interpolate_range_image(range_image: Union[np.ndarray, torch.Tensor], method
         x = x.to(device)
     x = x.to(torch.float32).contiguous()
     out = torch.empty_like(x)
+    if x.shape[2] != _lib.N_AZIMUTH:             # other widths: the general kernel
+        p = _lib.NscParams()
+        lib.nsc_default_params(C.byref(p))
+        p.n_azimuth, p.n_elevation, p.target_rows, p.n_bins = int(x.shape[2]), int(x.shape[1]), 1, 1
+        if x.shape[0]:
+            _anywidth_images(x, p, None, 1 if method == "nearest" else 0, None, out)
+        if single:
+            out = out[0]
+        return out.cpu().numpy() if is_np else out
     with torch.cuda.device(x.device):
         st = lib.nsc_interpolate_range_images(x.data_ptr(), x.shape[0], x.shape[1],
                                               1 if method == "nearest" else 0, out.data_ptr(),

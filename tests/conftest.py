@@ -10,7 +10,7 @@ if ROOT not in sys.path:
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 # golden files that hold a point cloud and the reference's outputs for it
 POINT_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN_DIR)
-                     if f.endswith(".npz") and not f.startswith(("forward_", "retrieval", "quantization", "intensity", "ctor_", "interp_", "keyframe")))
+                     if f.endswith(".npz") and not f.startswith(("forward_", "retrieval", "quantization", "intensity", "ctor_", "interp_", "keyframe", "widths")))
 
 
 def pytest_configure(config):

@@ -565,3 +565,43 @@ def test_graft_entry_smoke_passes():
     """The driver's smoke() entry point, so that the suite catches a regression of it."""
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+def test_other_image_widths_against_reference_vectors():
+    """n_azimuth other than 360 runs the general kernel (csrc/nsc_anywidth.cu): same parity bars
+    as the 360-column path against vectors recorded from the unmodified reference
+    (tests/golden/widths.npz): image bit-exact on the cloud stripped of edge points,
+    interpolation bit-exact for both methods, descriptors to rtol 1e-4 / atol 1e-7."""
+    from neural_spectral_codec_b200 import SpectralEncoder, interpolate_range_image
+    g = np.load(os.path.join(GOLDEN_DIR, "widths.npz"))
+    for i in range(int(g["n_configs"])):
+        kw = eval(str(g[f"c{i}_kw"]))
+        enc = SpectralEncoder(**kw).cuda()
+        cfg = orc.OracleConfig(**kw)
+        pts = g[f"c{i}_points"]
+        np.testing.assert_array_equal(enc.freq_to_bin(), g[f"c{i}_lut"])
+        # the unstripped cloud: at most one pixel per excused point; descriptor close
+        img = enc.projector.project(pts, keep_intensity=False)[0]
+        d_az, d_el = orc.edge_distance(pts, cfg)
+        n_amb = int(((d_az <= 1e-5) | (d_el <= 1e-5)).sum())
+        assert (img != g[f"c{i}_image"]).sum() <= 2 * n_amb
+        assert np.abs(enc.encode_points(pts).cpu().numpy() - g[f"c{i}_desc"]).max() < 1e-4
+        # stripped cloud: bit-exact image, test-suite tolerances on the descriptor
+        st = orc.strip_ambiguous(pts, cfg)
+        ref = orc.stages(st, cfg)
+        dpts = torch.from_numpy(st).cuda()
+        offs = torch.tensor([0, len(st)])
+        np.testing.assert_array_equal(enc.projector.project_batch(dpts, offs)[0].cpu().numpy(), ref["range_image"])
+        if cfg.interpolate_empty:
+            np.testing.assert_array_equal(enc.projector.project_batch(dpts, offs, interpolate=True)[0].cpu().numpy(),
+                                          ref["interpolated"])
+        assert_descriptor(enc.encode_points(st).cpu().numpy(), ref["descriptor"])
+        assert_descriptor(enc.encode_scans([st, st[: len(st) // 2]])[0], ref["descriptor"])
+        # forward() on images and both interpolation methods
+        imgs = g[f"c{i}_imgs"]
+        fwd = enc(torch.from_numpy(imgs).cuda()).cpu().numpy()
+        for j in range(len(imgs)):
+            assert_descriptor(fwd[j], g[f"c{i}_forward"][j])
+        np.testing.assert_array_equal(interpolate_range_image(imgs), g[f"c{i}_linear"])
+        np.testing.assert_array_equal(interpolate_range_image(imgs, method="nearest"), g[f"c{i}_nearest"])
+        np.testing.assert_array_equal(interpolate_range_image(imgs[0]), g[f"c{i}_linear"][0])

@@ -153,3 +153,22 @@ def test_oracle_interpolation_matches_reference_on_random_sparse_images():
     for img, want, near in zip(g["images"], g["interpolated"], g["nearest"]):
         np.testing.assert_array_equal(orc.interpolate_range_image(img), want)
         np.testing.assert_array_equal(orc.interpolate_range_image(img, method="nearest"), near)
+
+
+def test_oracle_reproduces_the_reference_at_other_widths():
+    """n_azimuth other than 360 (tests/golden/make_golden_widths.py): projection, interpolation
+    (both methods), freq->bin table, descriptor and forward() batches."""
+    g = np.load(os.path.join(GOLDEN_DIR, "widths.npz"))
+    for i in range(int(g["n_configs"])):
+        kw = eval(str(g[f"c{i}_kw"]))
+        cfg = orc.OracleConfig(**{k: v for k, v in kw.items()})
+        st = orc.stages(g[f"c{i}_points"], cfg)
+        np.testing.assert_array_equal(st["range_image"], g[f"c{i}_image"])
+        np.testing.assert_array_equal(orc.interpolate_range_image(g[f"c{i}_image"]), g[f"c{i}_filled"])
+        np.testing.assert_array_equal(st["freq_to_bin"], g[f"c{i}_lut"])
+        np.testing.assert_allclose(st["descriptor"], g[f"c{i}_desc"], rtol=1e-6, atol=1e-9)
+        np.testing.assert_allclose(orc.encode_batch(torch.from_numpy(g[f"c{i}_imgs"]), cfg).numpy(), g[f"c{i}_forward"],
+                                   rtol=1e-6, atol=1e-9)
+        for img, lin, near in zip(g[f"c{i}_imgs"], g[f"c{i}_linear"], g[f"c{i}_nearest"]):
+            np.testing.assert_array_equal(orc.interpolate_range_image(img), lin)
+            np.testing.assert_array_equal(orc.interpolate_range_image(img, method="nearest"), near)
