@@ -225,8 +225,9 @@ int nsc_pipeline_encode(nsc_pipeline* pl, const float* h_points, int point_strid
 /* ONE scan from pageable host memory to a descriptor on the DEVICE, on the caller's stream -- the
  * reference's own call shape: encoder.encode_points(numpy_scan) per scan (pipeline.py:245,
  * :336-354, train_multi_dataset.py:182), whose result lives on alpha.device. The scan is staged
- * through pinned memory in pieces that overlap with their DMA; the fused kernel follows on
- * `stream`. Returns as soon as h_points may be reused; d_out (float32[target_rows * n_bins]) is
+ * through pinned memory in 256 KB pieces by the calling thread and up to three threads the
+ * pipeline keeps for this, each piece going to the copy engine as soon as it is staged; the fused
+ * kernel follows on `stream`. Returns as soon as h_points may be reused; d_out (float32[target_rows * n_bins]) is
  * complete in stream order. n_points <= max_chunk_points of the pipeline. */
 int nsc_pipeline_encode_scan(nsc_pipeline* pl, const float* h_points, int point_stride, int64_t n_points,
                              const nsc_params* p, const int32_t* h_lut, float* d_out, void* stream);
