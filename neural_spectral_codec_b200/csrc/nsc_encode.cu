@@ -1,7 +1,13 @@
-// Fused encode kernel: points -> min-range image (shared memory) -> interpolation -> spectrum
-// -> descriptor. One persistent CTA per resident slot; each CTA pulls whole scans from a work
-// counter, so the range image, its interpolation and the spectrum never leave shared memory:
-// HBM traffic is the 16 B per point and the descriptor.
+// Fused encode kernels: points -> min-range image (shared memory) -> interpolation -> spectrum
+// -> descriptor. Persistent CTAs pull whole scans from a work counter, so the range image, its
+// interpolation and the spectrum never leave shared memory: HBM traffic is the 16 B per point
+// and the descriptor. Three kernels share the per-point and the tail code:
+//   encode_points_ws_kernel     the hot one (large batches of 16-byte points): one 1024-thread CTA
+//                               per SM, a TMA producer thread, 24 stream warps, 7 tail warps, two
+//                               images; see the comment above it
+//   encode_points_kernel        generic: 2 x 512-thread CTAs per SM, every warp streams and then runs
+//                               the tail (12-byte points, images too large to keep twice, A/B feeds)
+//   encode_points_split_kernel  small batches: one thread-block cluster per scan
 #include <stdlib.h>
 #include <string.h>
 
@@ -47,7 +53,8 @@ struct EncodeArgs {
     unsigned* part_image;        // one E x 361 key image per split scan (0xffffffff before the launch)
 };
 
-// How the point pass is fed from HBM.
+// How the point pass of the GENERIC kernel is fed from HBM (the warp-specialised kernel has its own
+// whole-stage TMA ring).
 //   kFeedCpAsync  per-thread ring of 16-byte cp.async copies (SASS LDGSTS): kCpDepth-1 stages in
 //                 flight per thread without holding registers; needs 16-byte points.
 //   kFeedLdg      plain vector loads into registers (3-float points; A/B with NSC_FEED=ldg).
