@@ -87,6 +87,9 @@ struct PeerFlags {
 __global__ void peer_signal_wait_kernel(PeerFlags f, int n_peers, int rank, uint32_t signal_value,
                                         uint32_t wait_value) {
     const int p = threadIdx.x;
+    // programmatic dependent of the encode kernel: set up while that grid drains, released when
+    // it has completed and its (peer) stores are flushed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (p >= n_peers) return;
     __threadfence_system();
     uint32_t* theirs = f.ptr[p] + rank;
@@ -108,8 +111,16 @@ int nsc_peer_signal_wait(uint32_t* const* h_peer_flags, int n_peers, int rank, u
         f.ptr[i] = i < n_peers ? h_peer_flags[i] : nullptr;
         if (i < n_peers && !f.ptr[i]) return NSC_ERR_NULL_POINTER;
     }
-    peer_signal_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(f, n_peers, rank, signal_value, wait_value);
-    return record_cuda(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3(32);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return record_cuda(cudaLaunchKernelEx(&cfg, peer_signal_wait_kernel, f, n_peers, rank, signal_value, wait_value));
 }
 
 int nsc_project_batch(const float* d_points, int point_stride, const int64_t* d_offsets,

@@ -781,6 +781,9 @@ encode_points_ws_kernel(const __grid_constant__ EncodeArgs a, const __grid_const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const WsLayout L(dp.E, dp.T, dp.n_bins);
     const int tid = threadIdx.x;
+    // a kernel enqueued as a programmatic dependent (the signal-and-wait of a multi-GPU step) may
+    // be set up from now on; it still waits for this grid to complete before it does anything
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (tid == 0) {
         volatile int* mail = reinterpret_cast<volatile int*>(smem_raw + L.mail_off);
         const WsBars bars(smem_u32(smem_raw + L.mbar_off));

@@ -135,6 +135,7 @@ wasserstein_kernel(const __grid_constant__ QueryArgs a) {
     const long long n_warps = (long long)gridDim.x * kRWarps;
     const long long r0 = (long long)blockIdx.x * kRWarps + warp;
     const bool vec = (a.n_bins & 3) == 0;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the selection may become resident now
     if (a.n_bins < padded)
         for (int s = 0; s < kRowStages; ++s)
             for (int e = a.n_bins + lane; e < padded; e += 32) ring[s * padded + e] = 0.0f;
@@ -278,6 +279,9 @@ select_kernel(const __grid_constant__ SelectArgs a) {
     __shared__ int s_last, s_count, s_valid;
     const int q = blockIdx.y, g = blockIdx.x, tid = threadIdx.x;
     const unsigned kInf = 0x7f800000u;
+    // launched as a programmatic dependent of the distance pass: resident early, released when that
+    // grid has completed and its writes are visible
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     // 1. bound: k-th smallest of 256 group minima (each group = the rows of some warps)
     unsigned long long m = ~0ull;
     {
@@ -721,8 +725,18 @@ int nsc_wasserstein_query(const float* d_query_hists, int n_queries, const float
             sa.top_count = d_top_count;
             long long per_q = (n_db + 4 * kSelThreads - 1) / (4 * kSelThreads);      // ~1024 rows per CTA
             const int ctas = (int)(per_q < 1 ? 1 : per_q > kSelCtas ? kSelCtas : per_q);
-            select_kernel<<<dim3(ctas, n_queries), kSelThreads, 0, s>>>(sa);
-            return record_cuda(cudaGetLastError());
+            // programmatic dependent launch: the grid is set up while the distance pass drains
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(ctas, n_queries);
+            cfg.blockDim = dim3(kSelThreads);
+            cfg.dynamicSmemBytes = 0;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            return record_cuda(cudaLaunchKernelEx(&cfg, select_kernel, sa));
         }
         topk_kernel<<<n_queries, kTopThreads, 0, s>>>(t);
         return record_cuda(cudaGetLastError());
