@@ -835,6 +835,59 @@ def run_keyframe(args):
     emit(line)
 
 
+# ----------------------------------------------------------------------------- wire format (secondary)
+def run_quantize(args):
+    """Secondary workload: the uint16 wire format of a 100 k x 800 database
+    (encoding/quantization.py:131-192, generalised from 50 to 800 bins): quantise + dequantise."""
+    import numpy as np
+    import torch
+
+    from neural_spectral_codec_b200.quantization import HistogramQuantizer
+    dev = torch.device("cuda")
+    n = args.db
+    g = torch.Generator(device=dev).manual_seed(3)
+    h = torch.rand((n, 800), generator=g, device=dev) ** 4
+    h /= h.sum(1, keepdim=True)
+    qz = HistogramQuantizer(n_bins=800, device=dev)
+    for _ in range(3):
+        q = qz.quantize(h)
+    torch.cuda.synchronize()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(args.steps):
+        q = qz.quantize(h)
+    e1.record()
+    for _ in range(args.steps):
+        d = qz.dequantize(q)
+    e2.record()
+    torch.cuda.synchronize()
+    ms_q, ms_d = e0.elapsed_time(e1) / args.steps, e1.elapsed_time(e2) / args.steps
+    peak, _ = hbm_peak()
+    bytes_q = n * 800 * (4 + 2)
+    line = {"metric": "descriptors_quantised_per_sec", "value": n / (ms_q * 1e-3), "unit": "descriptors/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": 3, "ms_per_step": ms_q, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 -> u16", "data": "synthetic",
+            "config": {"workload": f"uint16 quantisation of {n} x 800 descriptors (sum of a row = 65535 exactly)",
+                       "dequantise_ms": ms_d},
+            "roofline": {"bound": "hbm", "achieved": bytes_q / (ms_q * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bytes_q / (ms_q * 1e-3) / 1e9 / peak, "traffic": None,
+                         "dequantise_frac": bytes_q / (ms_d * 1e-3) / 1e9 / peak},
+            "gpu_launches": 2 * args.steps,
+            "checks": {"row_sums_65535": bool((q.to(torch.int32).sum(1) == 65535).all().item()),
+                       "max_roundtrip_error": float((d - h).abs().max().item())}}
+    if not args.no_cpu:
+        from oracle import quantization_oracle as qo
+        hc = h[:2000].cpu().numpy()
+        t0 = time.perf_counter()
+        want = np.stack([qo.quantize(r) for r in hc])
+        cpu_s = (time.perf_counter() - t0) / len(hc)
+        line["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "descriptors/s", "cores": 1, "kind": "port",
+                                "sample": f"{len(hc)} rows, oracle/quantization_oracle.py (the reference's quantiser "
+                                          "is hard-wired to 50 bins)"}
+        line["checks"]["equal_to_cpu"] = bool(np.array_equal(want, q[:2000].cpu().numpy()))
+    emit(line)
+
+
 def emit(line: dict) -> None:
     """The one JSON line goes to the REAL stdout; everything else a library prints to fd 1
     (e.g. NCCL's version banner) was redirected to stderr in main()."""
@@ -868,7 +921,7 @@ def main():
     ap.add_argument("--shape", default="hdl64", choices=sorted(SHAPE_DESC),
                     help="sensor shape of the synthetic scans (BASELINE.json configs 2-4; default = the metric's config)")
     ap.add_argument("--shuffle", action="store_true", help="random point order inside each scan")
-    ap.add_argument("--workload", default="encode", choices=["encode", "retrieval", "keyframe"],
+    ap.add_argument("--workload", default="encode", choices=["encode", "retrieval", "keyframe", "quantize"],
                     help="encode = the BASELINE.json metric (default); retrieval / keyframe = secondary lines "
                          "for the stage-1 retrieval and the keyframe-gate voxel IoU")
     ap.add_argument("--pairs", type=int, default=512, help="keyframe: cloud pairs per launch")
@@ -884,6 +937,8 @@ def main():
         run_retrieval(args)
     elif args.workload == "keyframe":
         run_keyframe(args)
+    elif args.workload == "quantize":
+        run_quantize(args)
     else:
         run_gpu_arm(args)
 
