@@ -25,6 +25,10 @@ Prints ONE JSON line (rank 0):
                 git-ignored copy made by oracle/make_ref.py is present, else the oracle port)
 
 ``--impl reference`` times that same CPU encoder as the reference arm, honouring --steps/--warmup.
+
+Secondary lines (not the BASELINE.json metric, same JSON shape): ``--workload retrieval`` (stage-1
+Wasserstein top-K over a 100 k x 800 database), ``--workload keyframe`` (voxel IoU of the keyframe
+gate), ``--workload quantize`` (uint16 wire format).
 """
 import argparse
 import json
