@@ -59,6 +59,62 @@ def test_cuda_quantiser_is_bit_exact(golden, n_bins):
 
 
 @pytest.mark.gpu
+def test_cuda_quantiser_unaligned_rows_take_the_scalar_path(golden):
+    """Rows that do not start on 16-byte boundaries (a view shifted by one element) cannot use the
+    16-byte row moves; the result is the same bits."""
+    from neural_spectral_codec_b200.quantization import HistogramQuantizer
+    h, q, d = golden["hist800"], golden["quant800"], golden["deq800"]
+    qz = HistogramQuantizer(n_bins=800)
+    buf = torch.zeros(h.size + 1, dtype=torch.float32, device="cuda")
+    buf[1:] = torch.from_numpy(h).cuda().flatten()
+    shifted = buf[1:].view(h.shape)
+    assert shifted.data_ptr() % 16 != 0
+    got = qz.quantize(shifted)
+    assert torch.equal(got.cpu().to(torch.int32), torch.from_numpy(q.astype(np.int32)))
+    qbuf = torch.zeros(q.size + 1, dtype=torch.uint16, device="cuda")
+    qbuf[1:] = got.flatten()
+    qshift = qbuf[1:].view(q.shape)
+    assert qshift.data_ptr() % 16 != 0
+    assert torch.equal(qz.dequantize(qshift).cpu(), torch.from_numpy(d))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_bins", (800, 2896, 50))
+def test_cuda_quantiser_unusual_rows(n_bins):
+    """Rows outside the descriptor regime (the kernel divides those the long way): a negative
+    element, huge and tiny sums, an all-zero row, one spike, zeros and denormals between ordinary
+    values, a row below epsilon. Same integers / floats as the oracle."""
+    from neural_spectral_codec_b200.quantization import HistogramQuantizer
+    rng = np.random.default_rng(n_bins)
+    base = (rng.random((10, n_bins)) ** 4).astype(np.float32)
+    base /= base.sum(1, keepdims=True)
+    rows = base.copy()
+    rows[0, 5] = -1e-9                                   # sign bit set, rounds to 0 on both sides
+    rows[1] *= np.float32(1e15)                          # sum beyond the moderate range
+    rows[2] *= np.float32(1e-6)                          # small but moderate sum
+    rows[3] = 0.0                                        # nothing to normalise, nothing to fix up
+    rows[4] = 0.0
+    rows[4, n_bins // 3] = 0.75                          # one spike takes all 65535
+    rows[5, ::3] = 0.0
+    rows[5, 1::7] = np.float32(1e-42)                    # denormals
+    rows[6] *= np.float32(1e-9)                          # sum <= epsilon: not normalised
+    rows[7] *= np.float32(3e-13)                         # far below epsilon
+    rows[8, :] = np.float32(1.0 / n_bins)                # the uniform fallback descriptor
+    rows[9] *= np.float32(2.0 ** 30)                     # large, still moderate
+    qz = HistogramQuantizer(n_bins=n_bins)
+    got = qz.quantize(rows)
+    want = np.stack([qo.quantize(r) for r in rows])
+    np.testing.assert_array_equal(got, want)
+    back = qz.dequantize(got)
+    np.testing.assert_array_equal(back, np.stack([qo.dequantize(r) for r in got]))
+    # dequantise rows the quantiser never emits: all zero (uniform fallback), a single count, all 65535
+    odd = np.zeros((3, n_bins), np.uint16)
+    odd[1, n_bins - 1] = 1
+    odd[2] = 65535
+    np.testing.assert_array_equal(qz.dequantize(odd), np.stack([qo.dequantize(r) for r in odd]))
+
+
+@pytest.mark.gpu
 def test_encoder_descriptors_round_trip():
     """encode -> quantise -> dequantise keeps the descriptor within one quantisation step and the
     retrieval ranking of the exact descriptors."""
