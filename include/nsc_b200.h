@@ -319,6 +319,14 @@ int nsc_test_host_classify(const float* h_points, int point_stride, int64_t n_po
                            const nsc_params* p, int32_t* h_row, int32_t* h_col, uint8_t* h_keep);
 /* 0 = polynomial row assignment, 1 = threshold search (wide fields of view); < 0 = status. */
 int nsc_test_row_mode(const nsc_params* p);
+/* The summation plan the quantiser kernels follow for rows of n_bins elements (host only, no CUDA
+ * call): leaves [leaf_start[l], leaf_start[l] + leaf_len[l]) for l < *n_leaves, each summed with
+ * NumPy's 8 strided accumulators, then *n_adds additions in single-assignment form -- addition t
+ * writes slot *n_leaves + t = slot add_a[t] + slot add_b[t], a leaf's slot being its index -- and the
+ * row sum is slot *result_slot. The arrays hold 64 entries. Lets the CPU-only suite check, for every
+ * row length, that the plan reproduces NumPy's pairwise float32 sum bit for bit. */
+int nsc_test_pairwise_sum_plan(int n_bins, int32_t* n_leaves, int32_t* n_adds, int32_t* result_slot,
+                               uint16_t* leaf_start, uint16_t* leaf_len, uint8_t* add_a, uint8_t* add_b);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,7 @@ SYMBOLS = {
                                    _VP, _VP, _VP, _VP, _SZ, _VP]),
     "nsc_quantize_histograms": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
     "nsc_dequantize_histograms": (_I, [_VP, _I64, _I, C.c_float, _VP, _VP]),
+    "nsc_test_pairwise_sum_plan": (_I, [_I, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "nsc_test_host_classify": (_I, [_VP, _I, _I64, _PP, _VP, _VP, _VP]),
     "nsc_test_row_mode": (_I, [_PP]),
 }

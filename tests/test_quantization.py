@@ -41,6 +41,63 @@ def test_record_layout_matches_reference(golden):
     np.testing.assert_array_equal(CompressedDescriptor.from_bytes(big.to_bytes()).histogram, golden["quant800"][0])
 
 
+def _kernel_sum_plan(n_bins):
+    """The plan the kernels follow (host-side hook of the C ABI; no CUDA call)."""
+    import ctypes as C
+    from neural_spectral_codec_b200 import _lib
+    lib = _lib.load()
+    n_leaves, n_adds, result = C.c_int32(), C.c_int32(), C.c_int32()
+    start, length = np.zeros(64, np.uint16), np.zeros(64, np.uint16)
+    add_a, add_b = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+    st = lib.nsc_test_pairwise_sum_plan(n_bins, C.byref(n_leaves), C.byref(n_adds), C.byref(result),
+                                        start.ctypes.data, length.ctypes.data, add_a.ctypes.data, add_b.ctypes.data)
+    return st, n_leaves.value, n_adds.value, result.value, start, length, add_a, add_b
+
+
+def _sum_like_the_kernel(row):
+    """csrc/nsc_quantize.cu numpy_sum, step for step in float32: per leaf 8 strided accumulators,
+    ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), the leaf's tail, then the plan's additions."""
+    f = np.float32
+    st, n_leaves, n_adds, result, start, length, add_a, add_b = _kernel_sum_plan(len(row))
+    assert st == 0
+    slots = np.zeros(128, np.float32)
+    for l in range(n_leaves):
+        a = row[start[l]:start[l] + length[l]]
+        if len(a) < 8:
+            res = f(-0.0)
+            for x in a:
+                res = f(res + x)
+        else:
+            body = len(a) - len(a) % 8
+            r = a[:8].copy()
+            for i in range(8, body, 8):
+                r = r + a[i:i + 8]
+            res = f(f(f(r[0] + r[1]) + f(r[2] + r[3])) + f(f(r[4] + r[5]) + f(r[6] + r[7])))
+            for x in a[body:]:
+                res = f(res + x)
+        slots[l] = res
+    for t in range(n_adds):
+        slots[n_leaves + t] = f(slots[add_a[t]] + slots[add_b[t]])
+    return slots[result]
+
+
+def test_kernel_sum_plan_is_numpys_pairwise_sum_for_every_row_length():
+    """The quantised integers are bit-exact only if the float32 row sum is NumPy's; the GPU tests pin
+    six row lengths against the reference, this one walks the kernels' plan for all 4096."""
+    rng = np.random.default_rng(0)
+    for n_bins in range(1, 4097):
+        row = (rng.random(n_bins) ** 6 * 10.0 ** rng.integers(-3, 4, n_bins)).astype(np.float32)
+        assert _sum_like_the_kernel(row).tobytes() == row.sum().tobytes(), n_bins
+    # an all-zero row sums to zero (the sign of that zero is not NumPy's for rows of -0.0; the kernels
+    # only compare the sum with epsilon and add epsilon to it, where the sign cannot matter)
+    for row in (np.array([-0.0], np.float32), np.array([0.0, -0.0], np.float32), np.zeros(800, np.float32)):
+        assert _sum_like_the_kernel(row) == row.sum() == 0.0
+    assert _kernel_sum_plan(0)[0] != 0 and _kernel_sum_plan(4097)[0] != 0
+    st, n_leaves, n_adds, result, start, length, _, _ = _kernel_sum_plan(800)
+    assert (st, n_leaves, n_adds, result) == (0, 8, 7, 14)
+    assert list(length[:8]) == [96, 104] * 4 and list(start[:3]) == [0, 96, 200]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("n_bins", SIZES)
 def test_cuda_quantiser_is_bit_exact(golden, n_bins):
